@@ -1,0 +1,410 @@
+#!/usr/bin/env python
+"""Headline benchmark: train it/s (render fwd+bwd) and render Mpix/s at 1 M Gaussians,
+1920x1080, SH degree 3, through the MsplatRender plugin (pointrix_b200).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config cfg4]
+
+One "step" = one training iteration of the render path on one view per GPU:
+MsplatRender.render_iter forward, then backward of <dL/dimg, img> with a fixed
+random dL/dimg into every Gaussian parameter (+ NCCL all-reduce of the parameter
+gradients / ndc gradients / radii when N > 1, views sharded by rank).
+
+`--impl reference` times the CPU-PyTorch restatement of the same math (the oracle) on
+the host cores on a bounded sample of the same workload (the reference has no CPU
+implementation of its own).
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "train it/s (fwd+bwd), 1M Gaussians @1080p"
+UNIT = "view-iterations/s"
+
+
+def env_int(k, d):
+    return int(os.environ.get(k, d))
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.idx), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_oracle_run(cfg_name: str, sample_P: int, steps: int, warmup: int):
+    """CPU-PyTorch execution of the same projection/SH/sort/blend math (the oracle) on a bounded sample."""
+    import torch
+
+    from oracle import msplat_oracle as O
+    from pointrix_b200 import scene
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    c, sc, cams = scene.make_config(cfg_name, P=sample_P, views=max(1, min(4, steps + warmup)))
+    dimg = scene.upstream_gradient(3, c["H"], c["W"])
+    times = []
+    for it in range(warmup + steps):
+        v = it % cams["extrinsic_matrix"].shape[0]
+        leaves = {k: t.clone().requires_grad_() for k, t in sc.items()}
+        t0 = time.perf_counter()
+        o = O.render_iter(c["H"], c["W"], cams["extrinsic_matrix"][v], cams["intrinsic_params"], cams["camera_center"][v],
+                          **leaves, sh_degree=3)
+        (o["rendered_features_split"]["rgb"] * dimg).sum().backward()
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+    full_P = scene.CONFIGS[cfg_name]["P"]
+    t_sample = sum(times) / len(times)
+    t_full = t_sample * full_P / sample_P  # linear extrapolation in #Gaussians (stated in `sample`)
+    return {"value": 1.0 / t_full, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"first {sample_P} of {full_P} Gaussians of {cfg_name} at {c['W']}x{c['H']}, fwd+bwd, "
+                      f"{t_sample:.2f} s/view measured, linearly extrapolated x{full_P // sample_P} to the full cloud",
+            "s_per_view_sample": t_sample}
+
+
+def run_reference(args):
+    rank = env_int("RANK", 0)
+    if rank != 0:
+        return
+    r = cpu_oracle_run(args.config, args.cpu_sample, max(1, min(args.steps, 3)), min(args.warmup, 1))
+    line = {"metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1000.0 / r["value"], "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
+            "config": {"workload": workload_name(args.config), "parallelism": "cpu"},
+            "cpu_baseline": r, "gpu_launches": 0,
+            "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def workload_name(cfg):
+    from pointrix_b200 import scene
+
+    c = scene.CONFIGS[cfg]
+    return (f"{cfg}: {c['P']} Gaussians, SH degree 3, {c['W']}x{c['H']}, C=3 rgb, white bg, orbit cameras; "
+            f"MsplatRender.render_iter fwd + bwd of <G,img> (one view per GPU per step)")
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--config", default="cfg4")
+    ap.add_argument("--cpu-sample", type=int, default=100_000)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-ref-gpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+
+    import pointrix_b200 as pb
+    from pointrix_b200 import _lib, scene
+
+    rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+    assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    W_, K = max(args.warmup, 3), args.steps
+
+    c, sc, cams = scene.make_config(args.config)
+    H, W, P, V = c["H"], c["W"], c["P"], c["views"]
+    params = {k: v.to(dev).requires_grad_() for k, v in sc.items()}
+    cams_d = {k: v.to(dev) for k, v in cams.items()}
+    dimg = scene.upstream_gradient(3, H, W).to(dev)
+    r = pb.parse_renderer({"name": "MsplatRender"}, white_bg=True, device=str(dev))
+    r.sh_degree = 3
+
+    def view_of(step):  # views sharded by rank
+        return (step * world + rank) % V
+
+    def step_fn(step, cam_src=cams_d, g_img=dimg):
+        v = view_of(step)
+        for p_ in params.values():
+            p_.grad = None
+        out = r.render_iter(H, W, cam_src["extrinsic_matrix"][v], cam_src["intrinsic_params"], cam_src["camera_center"][v], **params)
+        img = out["rendered_features_split"]["rgb"]
+        loss = (img * g_img).sum()
+        loss.backward()
+        if world > 1:
+            from pointrix_b200 import parallel
+
+            parallel.allreduce_step([p_.grad for p_ in params.values()], out["uv_points"].grad, out["radii"], world)
+        return loss, out
+
+    def sync():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timed region --------------------------------------------------
+    for s in range(W_):
+        step_fn(s)
+    sync()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    timer = _lib.KernelTimer()
+    _lib.set_timer(timer)
+    l0 = _lib.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sync()
+    e0.record()
+    for s in range(K):
+        loss, out = step_fn(W_ + s)
+    e1.record()
+    sync()
+    ms = e0.elapsed_time(e1)
+    launches = _lib.launch_count - l0
+    _lib.set_timer(None)
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = t.item()
+    value = world * K / (ms / 1e3)
+    kern = timer.summary()
+
+    # ---- forward-only render Mpix/s (second half of the BASELINE metric) -----------------
+    with torch.no_grad():
+        for s in range(3):
+            r.render_iter(H, W, cams_d["extrinsic_matrix"][view_of(s)], cams_d["intrinsic_params"], cams_d["camera_center"][view_of(s)], **params)
+        sync()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record()
+        for s in range(K):
+            v = view_of(s)
+            r.render_iter(H, W, cams_d["extrinsic_matrix"][v], cams_d["intrinsic_params"], cams_d["camera_center"][v], **params)
+        f1.record()
+        sync()
+        tf = torch.tensor([f0.elapsed_time(f1)], device=dev)
+        if world > 1:
+            dist.all_reduce(tf, op=dist.ReduceOp.MAX)
+        render_mpix = world * K * W * H / 1e6 / (tf.item() / 1e3)
+
+    # ---- end to end through the plugin with HOST buffers --------------------------------
+    # per step: pinned host -> device copy of that view's camera (extrinsic 4x4, intrinsics 4,
+    # centre 3) and of its dL/dimg [3,H,W]; device -> host read of the loss and visible count.
+    host = {"extrinsic_matrix": cams["extrinsic_matrix"].pin_memory(), "intrinsic_params": cams["intrinsic_params"].pin_memory(),
+            "camera_center": cams["camera_center"].pin_memory()}
+    host_dimg = scene.upstream_gradient(3, H, W).pin_memory()
+    res_host = torch.zeros(2, dtype=torch.float32).pin_memory()
+    h2d = (16 + 4 + 3) * 4 + host_dimg.numel() * 4
+    d2h = 8
+
+    def e2e_step(step):
+        v = view_of(step)
+        E = host["extrinsic_matrix"][v].to(dev, non_blocking=True)
+        I = host["intrinsic_params"].to(dev, non_blocking=True)
+        Cc = host["camera_center"][v].to(dev, non_blocking=True)
+        G = host_dimg.to(dev, non_blocking=True)
+        for p_ in params.values():
+            p_.grad = None
+        out = r.render_iter(H, W, E, I, Cc, **params)
+        img = out["rendered_features_split"]["rgb"]
+        loss = (img * G).sum()
+        loss.backward()
+        if world > 1:
+            from pointrix_b200 import parallel
+
+            parallel.allreduce_step([p_.grad for p_ in params.values()], out["uv_points"].grad, out["radii"], world)
+        res = torch.stack([loss.detach(), out["visibility"].sum().float()])
+        res_host.copy_(res, non_blocking=True)
+        torch.cuda.current_stream().synchronize()  # the caller consumes the result every step
+        return float(res_host[0])
+
+    for s in range(3):
+        e2e_step(s)
+    sync()
+    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    g0.record()
+    for s in range(K):
+        e2e_step(3 + s)
+    g1.record()
+    sync()
+    te = torch.tensor([g0.elapsed_time(g1)], device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = world * K / (te.item() / 1e3)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline bookkeeping (algorithmic bytes per SURVEY.md 8d / DESIGN.md) -----------
+    peaks = {}
+    pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(pk):
+        peaks = json.load(open(pk))
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)"
+    # N for the view the stages were measured on varies per view; use the mean over timed views
+    Ns = []
+    from pointrix_b200 import ops
+
+    with torch.no_grad():
+        for s in range(min(K, V)):
+            v = view_of(W_ + s)
+            uv, depth = ops.project_point(params["position"], cams_d["intrinsic_params"], cams_d["extrinsic_matrix"][v][:3].contiguous(), W, H, nearest=0.2)
+            vis = (depth != 0).reshape(-1)
+            cov = ops.compute_cov3d(params["scaling"], params["rotation"], vis)
+            _, _, tl = ops.ewa_project(params["position"], cov, cams_d["intrinsic_params"], cams_d["extrinsic_matrix"][v][:3].contiguous(), uv, W, H, vis)
+            Ns.append(int(tl.sum()))
+    N_mean = sum(Ns) / len(Ns)
+    Cch, S = 3, 12
+    tiles = ((W + 15) // 16) * ((H + 15) // 16)
+    passes = (32 + (tiles - 1).bit_length() + 7) // 8
+    alg = {
+        "pxb_fused_forward": P * (12 + 12 + 16 + 4 + 192 + 4 * S + 4 + 4 + 4),
+        "pxb_tile_scan": P * 8,
+        "pxb_sort_gaussian": P * 28 + N_mean * 12 + N_mean * (8 + 24 * passes) + N_mean * 8 + tiles * 8,
+        "pxb_blend_forward": N_mean * (4 + 4 * S) + 4 * (Cch + 2) * H * W,
+        "pxb_blend_backward": N_mean * (4 + 4 * S) + (4 * Cch + 8) * H * W + N_mean * 8 * (6 + Cch),
+        "pxb_fused_backward": P * (4 * S + 12 + 12 + 16 + 192 + 4 + 4 + 12 + 12 + 16 + 4 + 192 + 8),
+    }
+    stages = {}
+    for name, st in kern.items():
+        b = alg.get(name)
+        stages[name] = {"ms_avg": round(st["ms_avg"], 4), "calls": st["calls"],
+                        "share_of_step": round(st["ms_total"] / ms, 4)}
+        if b:
+            gbs = b / (st["ms_avg"] * 1e-3) / 1e9
+            stages[name].update({"alg_bytes": int(b), "achieved_gbs": round(gbs, 1), "frac_of_hbm_peak": round(gbs / hbm_peak, 4)})
+    dom = max(kern.items(), key=lambda kv: kv[1]["ms_total"])[0]
+    dom_gbs = alg[dom] / (kern[dom]["ms_avg"] * 1e-3) / 1e9
+    roofline = {"kernel": dom, "bound": "hbm", "achieved": round(dom_gbs, 1), "peak": hbm_peak, "unit": "GB/s",
+                "frac": round(dom_gbs / hbm_peak, 4), "traffic": None, "peak_source": peak_src,
+                "note": "blend kernels are FP32-issue/shared-memory bound, not HBM bound: see blend_issue_roofline"}
+    # blending as (pixel,Gaussian) pair tests against the FP32 issue bound
+    sm_clk = (clocks or {}).get("sm_mhz") or 1965.0
+    pair_bound = 148 * 128 * sm_clk * 1e6 / 16.0
+    pairs = 256.0 * N_mean
+    blend_issue = {}
+    for name in ("pxb_blend_forward", "pxb_blend_backward"):
+        if name in kern:
+            pps = pairs / (kern[name]["ms_avg"] * 1e-3)
+            blend_issue[name] = {"pairs_upper_per_launch": pairs, "pairs_per_s": pps, "bound_pairs_per_s": pair_bound,
+                                 "frac": round(pps / pair_bound, 4),
+                                 "note": "pairs = 256 x intersections (upper bound: early exit skips part of them)"}
+
+    line = {
+        "metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W_,
+        "ms_per_step": round(ms / K, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(args.config), "intersections_mean": N_mean,
+                   "parallelism": f"view-sharded dp{world}" + (", NCCL all-reduce of 59+2 floats/Gaussian + max(radii) per step" if world > 1 else ""),
+                   "cache": "inputs larger than L2 (236 MB Gaussian table + 48 MB records vs 126 MB L2); a different view every step"},
+        "render_mpix_s": round(render_mpix, 2),
+        "e2e": {"value": round(e2e_value, 3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+        "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "roofline_stages": stages,
+        "blend_issue_roofline": blend_issue,
+    }
+    if not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_oracle_run(args.config, args.cpu_sample, 2, 1)
+    if world == 1 and not args.no_ref_gpu:
+        line["ref_gpu"] = ref_gpu_run(args.config, min(K, 10))
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def ref_gpu_run(cfg_name, steps):
+    """The compiled unmodified reference CUDA (oracle/_ref) on the same GPU, same inputs:
+    reported beside our number, never part of it."""
+    try:
+        import torch
+
+        from oracle import ref_driver
+        from pointrix_b200 import scene
+
+        if not ref_driver.available():
+            return {"unavailable": "oracle/_ref not built"}
+        c, sc, cams = scene.make_config(cfg_name)
+        dev = torch.device("cuda", env_int("LOCAL_RANK", 0))
+        sc = {k: v.to(dev) for k, v in sc.items()}
+        cams = {k: v.to(dev) for k, v in cams.items()}
+        dimg = scene.upstream_gradient(3, c["H"], c["W"]).to(dev)
+
+        def one(v, bwd=True):
+            f = ref_driver.render_forward(c["H"], c["W"], cams["extrinsic_matrix"][v], cams["intrinsic_params"], cams["camera_center"][v], **sc)
+            if bwd:
+                ref_driver.render_backward(f, dimg, sc["position"], sc["opacity"], sc["scaling"], sc["rotation"], sc["shs"], cams["camera_center"][v])
+
+        res = {}
+        for mode, bwd in (("fwd_bwd", True), ("fwd", False)):
+            for s in range(2):
+                one(s % c["views"], bwd)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for s in range(steps):
+                one(s % c["views"], bwd)
+            e1.record()
+            torch.cuda.synchronize()
+            res[mode + "_ms"] = e0.elapsed_time(e1) / steps
+        return {"impl": "msplat reference CUDA (sm_100 build, -O3 --use_fast_math) driven in its own op order",
+                "it_per_s": 1e3 / res["fwd_bwd_ms"], "ms_fwd_bwd": res["fwd_bwd_ms"], "ms_fwd": res["fwd_ms"],
+                "render_mpix_s": c["W"] * c["H"] / 1e6 / (res["fwd_ms"] / 1e3)}
+    except Exception as e:  # never let the side measurement kill the bench line
+        return {"unavailable": repr(e)[:200]}
+
+
+if __name__ == "__main__":
+    main()

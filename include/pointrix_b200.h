@@ -1,0 +1,121 @@
+/*
+ * pointrix_b200 -- C ABI of the B200-native msplat render path.
+ *
+ * Drop-in boundary: these entry points are what a binding for the reference's
+ * 12 `msplat._C` functions (msplat/msplat/src/ext.cpp:14-25; C++ signatures in
+ * msplat/msplat/include/*.h) would call, expressed with plain device pointers,
+ * sizes and a CUDA stream -- no torch types.  Every function returns 0 on
+ * success, a cudaError_t value (>0) on a CUDA failure or a PXB_ERR_* code (<0)
+ * on a bad argument; nothing throws across the boundary.
+ *
+ * Ownership: the caller allocates every buffer (device memory unless stated);
+ * the library never allocates, frees or retains pointers.  Calls are
+ * asynchronous on `stream` (a cudaStream_t passed as void*).  Thread-safe as
+ * long as concurrent calls use distinct streams and workspaces.
+ *
+ * Layout conventions (all row-major, contiguous, fp32 unless stated):
+ *   xyz[P,3] scales[P,3] uquats[P,4] (w,x,y,z) opacity[P,1] intr[4]=(fx,fy,cx,cy)
+ *   extr[3,4] uv[P,2] depth[P,1] cov3d[P,6] conic[P,3] radius[P] i32 tiles[P] i32
+ *   visible[P] u8 (bool) or NULL = all visible.
+ *   Packed blend record rec[P,S]  = {u,v,A,B,C,opacity,f_0..f_{c-1},0-pad}, S = pxb_record_stride(c)
+ *   Packed gradient    grec[P,S]  = {du,dv,dA,dB,dC,dopacity,df_0..}; must be zeroed by the caller.
+ *   Both must be 16-byte aligned.
+ */
+#ifndef POINTRIX_B200_H
+#define POINTRIX_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PXB_ERR_BAD_ARG (-1)
+#define PXB_ERR_UNSUPPORTED (-2)
+#define PXB_ERR_WORKSPACE (-3)
+#define PXB_ERR_ALIGN (-4)
+#define PXB_MAX_CHANNELS_PER_PASS 26
+
+/* One-time per-process initialisation (constant tables).  Idempotent. */
+int pxb_init(void);
+
+/* ---- projection: replaces projectPointsForward/Backward
+ *      (msplat/msplat/include/project_point.h, src/project_point.cu:147-227) ---- */
+int pxb_project_point_forward(int P, const float* xyz, const float* intr, const float* extr, int W, int H,
+                              float nearest, float extent, float* uv, float* depth, void* stream);
+/* dL_dintr[4] / dL_dextr[12] may be NULL (camera does not require grad); when
+ * given they must be zeroed by the caller and are accumulated atomically. */
+int pxb_project_point_backward(int P, const float* xyz, const float* intr, const float* extr, const float* depth,
+                               const float* dL_duv, const float* dL_ddepth, float* dL_dxyz, float* dL_dintr,
+                               float* dL_dextr, void* stream);
+
+/* ---- 3D covariance: replaces computeCov3DForward/Backward
+ *      (include/compute_cov3d.h, src/compute_cov3d.cu:149-199) ---- */
+int pxb_compute_cov3d_forward(int P, const float* scales, const float* uquats, const uint8_t* visible, float* cov3d,
+                              void* stream);
+int pxb_compute_cov3d_backward(int P, const float* scales, const float* uquats, const uint8_t* visible,
+                               const float* dL_dcov3d, float* dL_dscales, float* dL_duquats, void* stream);
+
+/* ---- EWA projection: replaces EWAProjectForward/Backward
+ *      (include/ewa_project.h, src/ewa_project.cu:254-344) ---- */
+int pxb_ewa_project_forward(int P, const float* xyz, const float* cov3d, const float* intr, const float* extr,
+                            const float* uv, int W, int H, const uint8_t* visible, float* conic, int* radius,
+                            int* tiles, void* stream);
+int pxb_ewa_project_backward(int P, const float* xyz, const float* cov3d, const float* intr, const float* extr,
+                             const int* radius, const float* dL_dconic, float* dL_dxyz, float* dL_dcov3d,
+                             float* dL_dintr, float* dL_dextr, void* stream);
+
+/* ---- spherical harmonics: replaces computeSHForward/Backward
+ *      (include/compute_sh.h, src/compute_sh.cu:1696-1753); shs[P,C,D], D in {1,4,...,121} ---- */
+int pxb_compute_sh_forward(int P, int C, int D, const float* shs, const float* dirs, const uint8_t* visible,
+                           float* value, void* stream);
+int pxb_compute_sh_backward(int P, int C, int D, const float* shs, const float* dirs, const uint8_t* visible,
+                            const float* dL_dval, float* dL_dshs, float* dL_ddirs, void* stream);
+
+/* ---- tile binning: replaces torch.cumsum + computeGaussianKey + torch.sort +
+ *      torch.gather + computeTileGaussianRange
+ *      (msplat/msplat/sort_gaussian.py:42-52, include/sort_gaussian.h, src/sort_gaussian.cu:74-142) ---- */
+size_t pxb_binning_workspace_bytes(int P, long long N_cap, int W, int H);
+/* offsets_incl[P] = inclusive cumsum(tiles); *total_dev = offsets_incl[P-1] (device int). */
+int pxb_tile_scan(int P, const int* tiles, int* offsets_incl, int* total_dev, void* ws, size_t ws_bytes, void* stream);
+/* N = number of intersections (host value of *total_dev).  uv may be strided
+ * (uv_stride floats between Gaussians) so the packed record can be passed.
+ * idx_sorted[N] i32, tile_range[tiles,2] i32; keys_sorted_out[N] i64 optional (NULL to skip). */
+int pxb_sort_gaussian(int P, long long N, const float* uv, int uv_stride, const float* depth, const int* radius,
+                      const int* tiles, const int* offsets_incl, int W, int H, int* idx_sorted, int* tile_range,
+                      long long* keys_sorted_out, void* ws, size_t ws_bytes, void* stream);
+
+/* ---- alpha blending: replaces alphaBlendingForward/Backward
+ *      (include/alpha_blending.h, src/alpha_blending.cu:248-572) ---- */
+int pxb_record_stride(int C); /* S for C <= PXB_MAX_CHANNELS_PER_PASS channels, else -1 */
+int pxb_pack_records(int P, const float* uv, const float* conic, const float* opacity, const float* feature, int C,
+                     int c0, int cn, int S, float* rec, void* stream);
+int pxb_unpack_grads(int P, const float* grec, int S, int C, int c0, int cn, int accumulate, float* dL_duv,
+                     float* dL_dconic, float* dL_dopacity, float* dL_dfeature, void* stream);
+/* out[C,H,W], final_T[H,W], ncontrib[H,W] i32 */
+int pxb_blend_forward(const float* rec, int S, int C, const int* idx_sorted, const int* tile_range, float bg, int W,
+                      int H, float* final_T, int* ncontrib, float* out, void* stream);
+int pxb_blend_backward(const float* rec, int S, int C, const int* idx_sorted, const int* tile_range, float bg, int W,
+                       int H, const float* final_T, const int* ncontrib, const float* dL_dout, float* grec,
+                       void* stream);
+
+/* ---- fused per-Gaussian stages of MsplatRender.render_iter
+ *      (pointrix/model/renderer/msplat.py:94-139 forward; its autograd graph backward).
+ *      shs[P,16,3] (the point cloud's native layout), sh_degree in 0..3,
+ *      features = rgb(3) [+ depth] [+ extra[P,n_extra]].
+ *      d_cam[19] = dintr[4], dextr[12], dcamera_center[3] (zeroed by caller) or NULL. ---- */
+int pxb_fused_forward(int P, int sh_degree, const float* pos, const float* scales, const float* quats,
+                      const float* opacity, const float* shs, const float* extra, int n_extra, int with_depth,
+                      const float* intr, const float* extr, const float* cam_center, int W, int H, float nearest,
+                      float extent, int S, float* rec, float* depth, int* radius, int* tiles, void* stream);
+int pxb_fused_backward(int P, int sh_degree, const float* pos, const float* scales, const float* quats,
+                       const float* shs, int n_extra, int with_depth, const float* intr, const float* extr,
+                       const float* cam_center, int W, int H, int S, const float* depth, const int* radius,
+                       const float* grec, float* d_pos, float* d_scales, float* d_quats, float* d_opacity,
+                       float* d_shs, float* d_extra, float* d_ndc, float* d_cam, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* POINTRIX_B200_H */

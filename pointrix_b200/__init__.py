@@ -1,0 +1,22 @@
+"""pointrix_b200 -- B200-native (sm_100a) msplat render path behind pointrix's
+``MsplatRender`` plugin API.  See DESIGN.md / INTEGRATION.md.
+
+Importing this package loads ``libpointrix_b200.so`` (hand-written CUDA behind
+a C ABI, ``include/pointrix_b200.h``); there is no CPU or PyTorch fallback.
+"""
+from .ops import (  # noqa: F401
+    alpha_blending,
+    compute_cov3d,
+    compute_sh,
+    ewa_project,
+    project_point,
+    rasterization,
+    sort_gaussian,
+)
+from .registry import RENDERER_REGISTRY, parse_renderer  # noqa: F401
+from .renderer import MsplatRender, RenderFeatures, fused_render  # noqa: F401
+
+__all__ = [
+    "project_point", "compute_cov3d", "ewa_project", "sort_gaussian", "compute_sh", "alpha_blending",
+    "rasterization", "MsplatRender", "RenderFeatures", "RENDERER_REGISTRY", "parse_renderer", "fused_render",
+]

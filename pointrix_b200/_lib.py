@@ -1,0 +1,134 @@
+"""ctypes binding of libpointrix_b200.so (C ABI declared in include/pointrix_b200.h).
+
+There is no CPU fallback: if the library is missing the import fails loudly.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libpointrix_b200.so")
+
+ERRORS = {-1: "bad argument", -2: "unsupported configuration", -3: "workspace too small", -4: "pointer not 16-byte aligned"}
+
+p = C.c_void_p
+i32 = C.c_int
+i64 = C.c_longlong
+f32 = C.c_float
+sz = C.c_size_t
+
+# name -> (restype, argtypes); mirrors include/pointrix_b200.h one to one
+SIGNATURES = {
+    "pxb_init": (i32, []),
+    "pxb_project_point_forward": (i32, [i32, p, p, p, i32, i32, f32, f32, p, p, p]),
+    "pxb_project_point_backward": (i32, [i32, p, p, p, p, p, p, p, p, p, p]),
+    "pxb_compute_cov3d_forward": (i32, [i32, p, p, p, p, p]),
+    "pxb_compute_cov3d_backward": (i32, [i32, p, p, p, p, p, p, p]),
+    "pxb_ewa_project_forward": (i32, [i32, p, p, p, p, p, i32, i32, p, p, p, p, p]),
+    "pxb_ewa_project_backward": (i32, [i32, p, p, p, p, p, p, p, p, p, p, p]),
+    "pxb_compute_sh_forward": (i32, [i32, i32, i32, p, p, p, p, p]),
+    "pxb_compute_sh_backward": (i32, [i32, i32, i32, p, p, p, p, p, p, p]),
+    "pxb_binning_workspace_bytes": (sz, [i32, i64, i32, i32]),
+    "pxb_tile_scan": (i32, [i32, p, p, p, p, sz, p]),
+    "pxb_sort_gaussian": (i32, [i32, i64, p, i32, p, p, p, p, i32, i32, p, p, p, p, sz, p]),
+    "pxb_record_stride": (i32, [i32]),
+    "pxb_pack_records": (i32, [i32, p, p, p, p, i32, i32, i32, i32, p, p]),
+    "pxb_unpack_grads": (i32, [i32, p, i32, i32, i32, i32, i32, p, p, p, p, p]),
+    "pxb_blend_forward": (i32, [p, i32, i32, p, p, f32, i32, i32, p, p, p, p]),
+    "pxb_blend_backward": (i32, [p, i32, i32, p, p, f32, i32, i32, p, p, p, p, p]),
+    "pxb_fused_forward": (i32, [i32, i32, p, p, p, p, p, p, i32, i32, p, p, p, i32, i32, f32, f32, i32, p, p, p, p, p]),
+    "pxb_fused_backward": (i32, [i32, i32, p, p, p, p, i32, i32, p, p, p, i32, i32, i32, p, p, p, p, p, p, p, p, p, p, p, p]),
+}
+
+if not os.path.exists(LIB_PATH):
+    raise ImportError(
+        f"{LIB_PATH} is missing: pointrix_b200 has no CPU/PyTorch fallback. "
+        "Build it with `python -m pointrix_b200.csrc.build` (needs nvcc)."
+    )
+
+lib = C.CDLL(LIB_PATH)
+for _name, (_res, _args) in SIGNATURES.items():
+    _fn = getattr(lib, _name)  # AttributeError here means header and library disagree
+    _fn.restype = _res
+    _fn.argtypes = _args
+
+_initialised = False
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc == 0:
+        return
+    if rc < 0:
+        raise RuntimeError(f"pointrix_b200 {what}: {ERRORS.get(rc, rc)}")
+    raise RuntimeError(f"pointrix_b200 {what}: CUDA error {rc}")
+
+
+def ensure_init() -> None:
+    global _initialised
+    if not _initialised:
+        check(lib.pxb_init(), "pxb_init")
+        _initialised = True
+
+
+# ---------------------------------------------------------------------------
+# launch accounting: every C-ABI call of the package goes through launch().
+# ---------------------------------------------------------------------------
+# kernels launched per entry point (memsets not counted); sort adds its radix passes
+KERNELS_PER_CALL = {
+    "pxb_project_point_forward": 1, "pxb_project_point_backward": 1, "pxb_compute_cov3d_forward": 1,
+    "pxb_compute_cov3d_backward": 1, "pxb_ewa_project_forward": 1, "pxb_ewa_project_backward": 1,
+    "pxb_compute_sh_forward": 1, "pxb_compute_sh_backward": 1, "pxb_tile_scan": 1, "pxb_sort_gaussian": 4,
+    "pxb_pack_records": 1, "pxb_unpack_grads": 1, "pxb_blend_forward": 1, "pxb_blend_backward": 1,
+    "pxb_fused_forward": 1, "pxb_fused_backward": 1,
+}
+
+
+class KernelTimer:
+    """CUDA-event timer around each C-ABI call (events are recorded on the stream the
+    kernels are launched on: PyTorch's current stream)."""
+
+    def __init__(self):
+        self.events = []  # (name, e0, e1)
+        self.launches = 0
+
+    def summary(self):
+        import collections
+
+        tot, cnt = collections.OrderedDict(), collections.Counter()
+        for name, e0, e1 in self.events:
+            tot[name] = tot.get(name, 0.0) + e0.elapsed_time(e1)
+            cnt[name] += 1
+        return {k: {"ms_total": v, "calls": cnt[k], "ms_avg": v / cnt[k]} for k, v in tot.items()}
+
+
+_timer = None
+launch_count = 0
+
+
+def set_timer(t):
+    global _timer
+    _timer = t
+
+
+def launch(name: str, *args) -> None:
+    global launch_count
+    fn = getattr(lib, name)
+    n = KERNELS_PER_CALL.get(name, 1)
+    if name == "pxb_sort_gaussian":
+        W, H = args[8], args[9]
+        nt = ((W + 15) // 16) * ((H + 15) // 16)
+        n += (32 + max(nt - 1, 0).bit_length() + 7) // 8 if args[1] > 0 else -4
+    launch_count += n
+    if _timer is None:
+        check(fn(*args), name)
+        return
+    import torch
+
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    rc = fn(*args)
+    e1.record()
+    _timer.events.append((name, e0, e1))
+    _timer.launches += n
+    check(rc, name)

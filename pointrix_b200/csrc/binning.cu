@@ -1,0 +1,465 @@
+// Tile binning (reference: msplat/msplat/sort_gaussian.py:42-52 and
+// msplat/msplat/src/sort_gaussian.cu:17-71):
+//   1. inclusive prefix sum of tiles-touched        (torch.cumsum in the reference)
+//   2. key emission: key = tile<<32 | depth bits, value = Gaussian id, emitted
+//      in ascending Gaussian id / row-major tile order, warp-cooperatively so
+//      every store is coalesced and big Gaussians do not serialise one thread
+//   3. stable LSD radix sort of (key,value) pairs, onesweep style (one global
+//      histogram pass, then one read + one write of the pairs per 8-bit digit
+//      with decoupled look-back), restricted to the 32 + ceil(log2 tiles) key
+//      bits that can be non-zero                    (torch.sort + gather in the reference)
+//   4. per-tile [first,last) ranges from the sorted keys.
+// Integer work throughout: results are bit-identical to the reference's.
+#include "common.cuh"
+#include "pointrix_b200.h"
+
+namespace pxb {
+
+// ---------------------------------------------------------------------------
+// 1. single-pass inclusive scan (decoupled look-back), int32
+// ---------------------------------------------------------------------------
+constexpr int kScanThreads = 256;
+constexpr int kScanItems = 8;
+constexpr int kScanTile = kScanThreads * kScanItems;
+constexpr unsigned long long kFlagAgg = 1ull << 32, kFlagPrefix = 2ull << 32;
+
+__global__ void __launch_bounds__(kScanThreads)
+scan_kernel(int P, const int* __restrict__ in, int* __restrict__ out, int* __restrict__ total,
+            unsigned long long* status, unsigned int* ticket) {
+    __shared__ int s_warp[kScanThreads / 32];
+    __shared__ int s_tile, s_excl;
+    if (threadIdx.x == 0) s_tile = (int)atomicAdd(ticket, 1u);
+    __syncthreads();
+    const int tile = s_tile;
+    const int base = tile * kScanTile + threadIdx.x * kScanItems;
+    int v[kScanItems];
+    int sum = 0;
+#pragma unroll
+    for (int k = 0; k < kScanItems; k++) {
+        v[k] = (base + k < P) ? in[base + k] : 0;
+        sum += v[k];
+    }
+    // block exclusive scan of per-thread sums
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int n = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += n;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    int warp_off = 0, block_sum = 0;
+#pragma unroll
+    for (int w = 0; w < kScanThreads / 32; w++) {
+        const int s = s_warp[w];
+        if (w < warp) warp_off += s;
+        block_sum += s;
+    }
+    if (threadIdx.x == 0) {
+        volatile unsigned long long* st = status;
+        int excl = 0;
+        if (tile == 0) {
+            st[0] = kFlagPrefix | (unsigned int)block_sum;
+        } else {
+            st[tile] = kFlagAgg | (unsigned int)block_sum;
+            int t = tile - 1;
+            while (true) {
+                const unsigned long long s = st[t];
+                const unsigned int flag = (unsigned int)(s >> 32);
+                if (flag == 0) continue;
+                excl += (int)(unsigned int)s;
+                if (flag == 2) break;
+                t--;
+            }
+            st[tile] = kFlagPrefix | (unsigned int)(excl + block_sum);
+        }
+        s_excl = excl;
+        if ((tile + 1) * kScanTile >= P) *total = excl + block_sum;
+    }
+    __syncthreads();
+    int run = s_excl + warp_off + (incl - sum);
+#pragma unroll
+    for (int k = 0; k < kScanItems; k++) {
+        run += v[k];
+        if (base + k < P) out[base + k] = run;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// 2. key emission
+// ---------------------------------------------------------------------------
+constexpr int kEmitThreads = 256;
+
+__global__ void __launch_bounds__(kEmitThreads)
+emit_keys_kernel(int P, const float* __restrict__ uv, int uv_stride, const float* __restrict__ depth,
+                 const int* __restrict__ radius, const int* __restrict__ tiles, const int* __restrict__ offs_incl,
+                 int gx, int gy, long long N, unsigned long long* __restrict__ keys,
+                 unsigned int* __restrict__ vals) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    int x0 = 0, y0 = 0, w = 0, cnt = 0, off = 0;
+    unsigned int dbits = 0;
+    if (i < P) {
+        const int r = radius[i];
+        if (r > 0) {
+            int x1, y1;
+            tile_rect(uv[(size_t)i * uv_stride], uv[(size_t)i * uv_stride + 1], r, gx, gy, x0, y0, x1, y1);
+            w = x1 - x0;
+            cnt = w * (y1 - y0);
+            off = offs_incl[i] - tiles[i];  // cumsum(tiles)[i-1]  (sort_gaussian.cu:33)
+            dbits = __float_as_uint(depth[i]);
+        }
+    }
+    // warp-cooperative expansion: slot s of the warp's cnt-sum belongs to the lane
+    // whose inclusive prefix first exceeds s
+    int incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int n = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += n;
+    }
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    const int excl = incl - cnt;
+    for (int s = lane; s < ((total + 31) & ~31); s += 32) {
+        // binary search over the 32 inclusive prefixes (held one per lane)
+        int lo = 0;
+#pragma unroll
+        for (int step = 16; step > 0; step >>= 1) {
+            const int probe = __shfl_sync(0xffffffffu, incl, lo + step - 1);
+            if (probe <= s) lo += step;
+        }
+        // lo = first lane with incl > s   (s < total guarantees lo <= 31)
+        const int src = min(lo, 31);
+        const int e_src = __shfl_sync(0xffffffffu, excl, src);
+        const int x0s = __shfl_sync(0xffffffffu, x0, src);
+        const int y0s = __shfl_sync(0xffffffffu, y0, src);
+        const int ws = __shfl_sync(0xffffffffu, w, src);
+        const int offs = __shfl_sync(0xffffffffu, off, src);
+        const unsigned int db = __shfl_sync(0xffffffffu, dbits, src);
+        if (s < total) {
+            const int local = s - e_src;
+            const int row = local / ws, col = local - row * ws;
+            const long long tile_id = (long long)(y0s + row) * gx + (x0s + col);
+            const long long key = (tile_id << 32) | (long long)(int)db;  // sign-extending OR as the reference
+            const long long pos = (long long)offs + local;
+            if (pos >= 0 && pos < N) {
+                keys[pos] = (unsigned long long)key;
+                vals[pos] = (unsigned int)(blockIdx.x * blockDim.x + (threadIdx.x & ~31) + src);
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// 3. onesweep LSD radix sort, 8-bit digits, 64-bit keys + 32-bit values
+// ---------------------------------------------------------------------------
+constexpr int kRsThreads = 256;
+constexpr int kRsItems = 16;
+constexpr int kRsTile = kRsThreads * kRsItems;  // 4096 pairs per block
+constexpr int kRadix = 256;
+constexpr int kMaxPasses = 8;
+constexpr unsigned int kStAgg = 1u << 30, kStPrefix = 2u << 30, kStMask = (1u << 30) - 1u;
+
+__global__ void __launch_bounds__(kRsThreads)
+rs_histogram_kernel(const unsigned long long* __restrict__ keys, int N, int passes, unsigned int* __restrict__ hist) {
+    __shared__ unsigned int h[kMaxPasses][kRadix];
+    for (int k = threadIdx.x; k < kMaxPasses * kRadix; k += blockDim.x) (&h[0][0])[k] = 0;
+    __syncthreads();
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (long long)gridDim.x * blockDim.x) {
+        const unsigned long long k = keys[i];
+        for (int p = 0; p < passes; p++) atomicAdd(&h[p][(k >> (8 * p)) & 255u], 1u);
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < passes * kRadix; k += blockDim.x) {
+        const unsigned int c = (&h[0][0])[k];
+        if (c) atomicAdd(hist + k, c);
+    }
+}
+
+// exclusive scan over the 256 bins of every pass (one block per pass)
+__global__ void rs_scan_hist_kernel(unsigned int* __restrict__ hist) {
+    __shared__ unsigned int s_warp[kRadix / 32];
+    unsigned int* h = hist + blockIdx.x * kRadix;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned int c = h[threadIdx.x];
+    unsigned int incl = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned int n = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += n;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    unsigned int off = 0;
+    for (int w = 0; w < warp; w++) off += s_warp[w];
+    h[threadIdx.x] = off + incl - c;
+}
+
+struct RsSmem {
+    unsigned long long keys[kRsTile];
+    unsigned int vals[kRsTile];
+    unsigned int warp_hist[kRsThreads / 32][kRadix];
+    unsigned int digit_start[kRadix];
+    long long gbase[kRadix];
+    unsigned int warp_sums[kRadix / 32];
+    int tile;
+};
+
+__global__ void __launch_bounds__(kRsThreads)
+rs_onesweep_kernel(const unsigned long long* __restrict__ keys_in, const unsigned int* __restrict__ vals_in,
+                   unsigned long long* __restrict__ keys_out, unsigned int* __restrict__ vals_out, int N, int shift,
+                   const unsigned int* __restrict__ bin_base /*[256] exclusive*/, unsigned int* status,
+                   unsigned int* ticket) {
+    extern __shared__ __align__(16) unsigned char rs_raw[];
+    RsSmem& sm = *reinterpret_cast<RsSmem*>(rs_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) sm.tile = (int)atomicAdd(ticket, 1u);
+    for (int k = tid; k < (kRsThreads / 32) * kRadix; k += kRsThreads) (&sm.warp_hist[0][0])[k] = 0;
+    __syncthreads();
+    const int tile = sm.tile;
+    const long long tile_base = (long long)tile * kRsTile;
+    const int tile_n = (int)min((long long)kRsTile, (long long)N - tile_base);
+
+    // warp-striped load: item k of lane l in warp w sits at w*32*IPT + k*32 + l
+    unsigned long long key[kRsItems];
+    unsigned int val[kRsItems];
+    unsigned int rank[kRsItems];
+    const int wbase = warp * 32 * kRsItems + lane;
+#pragma unroll
+    for (int k = 0; k < kRsItems; k++) {
+        const int p = wbase + k * 32;
+        if (p < tile_n) {
+            key[k] = keys_in[tile_base + p];
+            val[k] = vals_in[tile_base + p];
+        } else {
+            key[k] = ~0ull;
+            val[k] = 0;
+        }
+    }
+    // warp-level stable ranking with match.any; counters private to the warp
+    const unsigned int lt_mask = (1u << lane) - 1u;
+    unsigned int* wh = sm.warp_hist[warp];
+#pragma unroll
+    for (int k = 0; k < kRsItems; k++) {
+        const bool valid = (wbase + k * 32) < tile_n;
+        const unsigned int d = (unsigned int)(key[k] >> shift) & 255u;
+        const unsigned int vmask = __ballot_sync(0xffffffffu, valid);
+        unsigned int peers = __match_any_sync(0xffffffffu, d) & vmask;
+        unsigned int old = 0;
+        int leader = 0;
+        if (valid) {
+            leader = __ffs(peers) - 1;
+            if (lane == leader) {
+                old = wh[d];
+                wh[d] = old + __popc(peers);
+            }
+        }
+        old = __shfl_sync(0xffffffffu, old, leader);
+        rank[k] = old + __popc(peers & lt_mask);
+        __syncwarp();
+    }
+    __syncthreads();
+    // per-digit: exclusive offsets across warps, tile total, publish for look-back
+    unsigned int count = 0;
+    {
+#pragma unroll
+        for (int w = 0; w < kRsThreads / 32; w++) {
+            const unsigned int c = sm.warp_hist[w][tid];
+            sm.warp_hist[w][tid] = count;
+            count += c;
+        }
+        volatile unsigned int* st = status + (size_t)tile * kRadix + tid;
+        *st = (tile == 0 ? kStPrefix : kStAgg) | count;
+    }
+    // exclusive scan of tile totals over digits -> start of each digit inside the sorted tile
+    {
+        unsigned int incl = count;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned int n = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += n;
+        }
+        if (lane == 31) sm.warp_sums[warp] = incl;
+        __syncthreads();
+        unsigned int off = 0;
+        for (int w = 0; w < warp; w++) off += sm.warp_sums[w];
+        sm.digit_start[tid] = off + incl - count;
+    }
+    // decoupled look-back: digits are independent, one thread per digit
+    {
+        unsigned int excl = 0;
+        if (tile > 0) {
+            int t = tile - 1;
+            while (true) {
+                const unsigned int s = *((volatile unsigned int*)(status + (size_t)t * kRadix + tid));
+                const unsigned int flag = s >> 30;
+                if (flag == 0) continue;
+                excl += s & kStMask;
+                if (flag == 2) break;
+                t--;
+            }
+            *((volatile unsigned int*)(status + (size_t)tile * kRadix + tid)) = kStPrefix | (excl + count);
+        }
+        sm.gbase[tid] = (long long)bin_base[tid] + (long long)excl - (long long)sm.digit_start[tid];
+    }
+    __syncthreads();
+    // scatter into tile-local sorted order
+#pragma unroll
+    for (int k = 0; k < kRsItems; k++) {
+        if ((wbase + k * 32) < tile_n) {
+            const unsigned int d = (unsigned int)(key[k] >> shift) & 255u;
+            const unsigned int pos = sm.digit_start[d] + sm.warp_hist[warp][d] + rank[k];
+            sm.keys[pos] = key[k];
+            sm.vals[pos] = val[k];
+        }
+    }
+    __syncthreads();
+    // coalesced write-out: consecutive sorted positions of one digit are consecutive in global memory
+#pragma unroll
+    for (int k = 0; k < kRsItems; k++) {
+        const int p = k * kRsThreads + tid;
+        if (p < tile_n) {
+            const unsigned long long kk = sm.keys[p];
+            const unsigned int d = (unsigned int)(kk >> shift) & 255u;
+            const long long dst = sm.gbase[d] + p;
+            keys_out[dst] = kk;
+            vals_out[dst] = sm.vals[p];
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// 4. tile ranges (sort_gaussian.cu:45-71)
+// ---------------------------------------------------------------------------
+__global__ void tile_range_kernel(int N, const unsigned long long* __restrict__ keys_sorted, int num_tiles,
+                                  int2* __restrict__ tile_range) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    const int cur = (int)(keys_sorted[i] >> 32);
+    if ((unsigned)cur >= (unsigned)num_tiles) return;  // negative-depth keys: undefined in the reference
+    if (i == 0) tile_range[cur].x = 0;
+    else {
+        const int prev = (int)(keys_sorted[i - 1] >> 32);
+        if (prev != cur) {
+            tile_range[cur].x = i;
+            if ((unsigned)prev < (unsigned)num_tiles) tile_range[prev].y = i;
+        }
+    }
+    if (i == N - 1) tile_range[cur].y = N;
+}
+
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+static inline int ceil_log2(int x) {
+    int b = 0;
+    while ((1ll << b) < x) b++;
+    return b;
+}
+static inline int sort_passes(int num_tiles) { return (32 + ceil_log2(num_tiles) + 7) / 8; }
+
+struct BinWs {
+    unsigned char* ctl;      // zeroed region: scan status/ticket, histograms, onesweep status/tickets
+    size_t ctl_bytes;
+    unsigned long long* scan_status;
+    unsigned int* scan_ticket;
+    unsigned int* hist;
+    unsigned int* rs_ticket;
+    unsigned int* rs_status;
+    unsigned long long* keys0;
+    unsigned long long* keys1;
+    unsigned int* vals_tmp;
+    size_t total;
+};
+
+static BinWs carve(void* ws, int P, long long Ncap, int num_tiles) {
+    BinWs b;
+    const int passes = sort_passes(num_tiles);
+    const size_t scan_tiles = (size_t)(P + kScanTile - 1) / kScanTile + 1;
+    const size_t rs_tiles = (size_t)((Ncap + kRsTile - 1) / kRsTile) + 1;
+    size_t o = 0;
+    unsigned char* base = (unsigned char*)ws;
+    b.ctl = base;
+    b.scan_status = (unsigned long long*)(base + o); o += align_up(scan_tiles * 8, 256);
+    b.scan_ticket = (unsigned int*)(base + o); o += 256;
+    b.hist = (unsigned int*)(base + o); o += align_up((size_t)kMaxPasses * kRadix * 4, 256);
+    b.rs_ticket = (unsigned int*)(base + o); o += 256;
+    b.rs_status = (unsigned int*)(base + o); o += align_up((size_t)passes * rs_tiles * kRadix * 4, 256);
+    b.ctl_bytes = o;
+    b.keys0 = (unsigned long long*)(base + o); o += align_up((size_t)Ncap * 8, 256);
+    b.keys1 = (unsigned long long*)(base + o); o += align_up((size_t)Ncap * 8, 256);
+    b.vals_tmp = (unsigned int*)(base + o); o += align_up((size_t)Ncap * 4, 256);
+    b.total = o;
+    return b;
+}
+
+}  // namespace pxb
+
+using namespace pxb;
+
+extern "C" {
+
+size_t pxb_binning_workspace_bytes(int P, long long N_cap, int W, int H) {
+    const int gx = (W + PXB_TILE - 1) / PXB_TILE, gy = (H + PXB_TILE - 1) / PXB_TILE;
+    if (N_cap < 1) N_cap = 1;
+    return carve(nullptr, P > 0 ? P : 1, N_cap, gx * gy).total;
+}
+
+// inclusive cumsum of tiles (int32) + total on the device
+int pxb_tile_scan(int P, const int* tiles, int* offsets_incl, int* total_dev, void* ws, size_t ws_bytes,
+                  void* stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    if (P <= 0) return (int)cudaMemsetAsync(total_dev, 0, sizeof(int), s);
+    const size_t scan_tiles = (size_t)(P + kScanTile - 1) / kScanTile + 1;
+    const size_t need = align_up(scan_tiles * 8, 256) + 256;
+    if (ws_bytes < need) return PXB_ERR_WORKSPACE;
+    unsigned long long* status = (unsigned long long*)ws;
+    unsigned int* ticket = (unsigned int*)((unsigned char*)ws + align_up(scan_tiles * 8, 256));
+    PXB_CUDA_OK(cudaMemsetAsync(ws, 0, need, s));
+    scan_kernel<<<(P + kScanTile - 1) / kScanTile, kScanThreads, 0, s>>>(P, tiles, offsets_incl, total_dev, status, ticket);
+    return (int)cudaGetLastError();
+}
+
+// keys + sort + ranges.  N = offsets_incl[P-1] (the caller has read it back).
+int pxb_sort_gaussian(int P, long long N, const float* uv, int uv_stride, const float* depth, const int* radius,
+                      const int* tiles, const int* offsets_incl, int W, int H, int* idx_sorted, int* tile_range,
+                      long long* keys_sorted_out /*nullable, [N]*/, void* ws, size_t ws_bytes, void* stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    const int gx = (W + PXB_TILE - 1) / PXB_TILE, gy = (H + PXB_TILE - 1) / PXB_TILE;
+    const int num_tiles = gx * gy;
+    PXB_CUDA_OK(cudaMemsetAsync(tile_range, 0, (size_t)num_tiles * 2 * sizeof(int), s));
+    if (P <= 0 || N <= 0) return 0;
+    if (N > 0x3fffffffll) return PXB_ERR_BAD_ARG;
+    BinWs b = carve(ws, P, N, num_tiles);
+    if (ws_bytes < b.total) return PXB_ERR_WORKSPACE;
+    const int passes = sort_passes(num_tiles);
+    const int rs_tiles = (int)((N + kRsTile - 1) / kRsTile);
+    PXB_CUDA_OK(cudaMemsetAsync(b.ctl, 0, b.ctl_bytes, s));
+    // choose the ping-pong start so that the last pass lands in idx_sorted
+    unsigned long long* kcur = b.keys0;
+    unsigned long long* kalt = b.keys1;
+    unsigned int* vcur = (passes % 2 == 0) ? (unsigned int*)idx_sorted : b.vals_tmp;
+    unsigned int* valt = (passes % 2 == 0) ? b.vals_tmp : (unsigned int*)idx_sorted;
+    emit_keys_kernel<<<(P + kEmitThreads - 1) / kEmitThreads, kEmitThreads, 0, s>>>(
+        P, uv, uv_stride, depth, radius, tiles, offsets_incl, gx, gy, N, kcur, vcur);
+    const int hist_blocks = (int)min((long long)(148 * 8), (N + kRsThreads * 8 - 1) / (kRsThreads * 8));
+    rs_histogram_kernel<<<hist_blocks, kRsThreads, 0, s>>>(kcur, (int)N, passes, b.hist);
+    rs_scan_hist_kernel<<<passes, kRadix, 0, s>>>(b.hist);
+    static bool attr_set = false;
+    if (!attr_set) {
+        PXB_CUDA_OK(cudaFuncSetAttribute(rs_onesweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RsSmem)));
+        attr_set = true;
+    }
+    for (int p = 0; p < passes; p++) {
+        rs_onesweep_kernel<<<rs_tiles, kRsThreads, sizeof(RsSmem), s>>>(
+            kcur, vcur, kalt, valt, (int)N, 8 * p, b.hist + p * kRadix,
+            b.rs_status + (size_t)p * (rs_tiles + 1) * kRadix, b.rs_ticket + p);
+        unsigned long long* tk = kcur; kcur = kalt; kalt = tk;
+        unsigned int* tv = vcur; vcur = valt; valt = tv;
+    }
+    tile_range_kernel<<<(int)((N + 255) / 256), 256, 0, s>>>((int)N, kcur, num_tiles, (int2*)tile_range);
+    if (keys_sorted_out)
+        PXB_CUDA_OK(cudaMemcpyAsync(keys_sorted_out, kcur, (size_t)N * 8, cudaMemcpyDeviceToDevice, s));
+    return (int)cudaGetLastError();
+}
+
+}  // extern "C"

@@ -1,0 +1,238 @@
+"""``MsplatRender`` -- the pointrix renderer plugin, B200-native.
+
+Drop-in for ``pointrix/model/renderer/msplat.py:12-248``: same registry entry
+name, ``Config``, ``setup``, ``render_iter`` / ``render_batch`` signatures and
+returned dict (``rendered_features_split`` / per-feature stacks, ``uv_points``,
+``visibility``, ``radii``), ``update_sh_degree``, ``state_dict`` /
+``load_state_dict``.  One view is five kernel launches forward (fused
+per-Gaussian stage, tile scan, key emit + radix sort + ranges, blend) and two
+backward (blend backward, fused per-Gaussian backward) instead of the
+reference's ~14 kernels + ~40 torch ops; the autograd graph of ``render_iter``
+(SURVEY.md section 8a "gradient routing") is reproduced by a single
+``torch.autograd.Function``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Dict, Optional
+
+import torch
+from torch import Tensor
+
+from . import ops
+from ._lib import launch, lib
+from .ops import _f32, _p, _stream
+from .registry import BaseObject, register_renderer
+
+
+class RenderFeatures:
+    """pointrix/model/renderer/utils/renderer_utils.py:4-71 -- per-Gaussian feature
+    tensors combined on the last dim in kwarg order, split back by channel count."""
+
+    def __init__(self, **kwargs) -> None:
+        for k, v in kwargs.items():
+            setattr(self, k, v)
+
+    def to(self, device) -> None:
+        for k, v in self.__dict__.items():
+            if isinstance(v, Tensor):
+                setattr(self, k, v.to(device))
+
+    def items(self):
+        return [(k, v) for k, v in self.__dict__.items() if isinstance(v, Tensor)]
+
+    def combine(self) -> Tensor:
+        return torch.cat([v for _, v in self.items()], dim=-1)
+
+    def split(self, feature: Tensor) -> Dict[str, Tensor]:
+        out, start = {}, 0
+        for k, v in self.items():
+            end = start + v.shape[-1]
+            out[k] = feature[start:end, ...]
+            start = end
+        return out
+
+
+class _FusedRender(torch.autograd.Function):
+    """render_iter's differentiable core: (Gaussians, camera) -> blended features."""
+
+    @staticmethod
+    def forward(ctx, position, opacity, scaling, rotation, shs, extra, intr, extr, cam_center, ndc, sh_degree, W, H,
+                bg, with_depth, nearest):
+        pos, op = _f32(position, "position"), _f32(opacity, "opacity")
+        sc, rot, sh = _f32(scaling, "scaling"), _f32(rotation, "rotation"), _f32(shs, "shs")
+        intr_c, extr_c, cc = _f32(intr, "intrinsic_params"), _f32(extr, "extrinsic_matrix"), _f32(cam_center, "camera_center")
+        ex = _f32(extra, "extra features") if extra is not None else None
+        dev = pos.device
+        P = pos.shape[0]
+        n_extra = 0 if ex is None else ex.shape[1]
+        Cc = 3 + int(with_depth) + n_extra
+        S = lib.pxb_record_stride(Cc)
+        W, H = int(W), int(H)
+        rec = torch.empty(max(P, 1), S, dtype=torch.float32, device=dev)
+        depth = torch.empty(max(P, 1), dtype=torch.float32, device=dev)
+        radius = torch.empty(P, dtype=torch.int32, device=dev)
+        tiles = torch.empty(max(P, 1), dtype=torch.int32, device=dev)
+        out = torch.empty(Cc, H, W, dtype=torch.float32, device=dev)
+        final_T = torch.empty(H, W, dtype=torch.float32, device=dev)
+        ncontrib = torch.empty(H, W, dtype=torch.int32, device=dev)
+        with torch.cuda.device(dev):
+            stream = _stream(dev)
+            launch("pxb_fused_forward", P, int(sh_degree), _p(pos), _p(sc), _p(rot), _p(op), _p(sh), _p(ex), n_extra,
+                                        int(with_depth), _p(intr_c), _p(extr_c), _p(cc), W, H, float(nearest), 1.3, S,
+                                        _p(rec), _p(depth), _p(radius), _p(tiles), stream)
+            idx_sorted, tile_range = ops._bin(rec, S, depth, radius, tiles, W, H)
+            launch("pxb_blend_forward", _p(rec), S, Cc, _p(idx_sorted), _p(tile_range), float(bg), W, H, _p(final_T),
+                                        _p(ncontrib), _p(out), stream)
+        ctx.save_for_backward(pos, sc, rot, sh, intr_c, extr_c, cc, rec, depth, radius, idx_sorted, tile_range, final_T,
+                              ncontrib)
+        ctx.meta = (int(sh_degree), W, H, float(bg), int(with_depth), n_extra, S, Cc,
+                    intr.shape, extr.shape, cam_center.shape, opacity.shape)
+        ctx.mark_non_differentiable(radius)
+        return out, radius
+
+    @staticmethod
+    def backward(ctx, d_out, _d_radius):
+        (pos, sc, rot, sh, intr, extr, cc, rec, depth, radius, idx_sorted, tile_range, final_T, ncontrib) = ctx.saved_tensors
+        sh_degree, W, H, bg, with_depth, n_extra, S, Cc, s_intr, s_extr, s_cc, s_op = ctx.meta
+        dev = pos.device
+        P = pos.shape[0]
+        g = _f32(d_out, "dL_drendered")
+        grec = torch.zeros(max(P, 1), S, dtype=torch.float32, device=dev)
+        d_pos = torch.empty_like(pos)
+        d_sc = torch.empty_like(sc)
+        d_rot = torch.empty_like(rot)
+        d_op = torch.empty(P, dtype=torch.float32, device=dev)
+        d_sh = torch.empty_like(sh)
+        d_extra = torch.empty(P, n_extra, dtype=torch.float32, device=dev) if n_extra > 0 else None
+        d_ndc = torch.empty(P, 2, dtype=torch.float32, device=dev)
+        need_cam = any(ctx.needs_input_grad[6:9])
+        d_cam = torch.zeros(19, dtype=torch.float32, device=dev) if need_cam else None
+        with torch.cuda.device(dev):
+            stream = _stream(dev)
+            launch("pxb_blend_backward", _p(rec), S, Cc, _p(idx_sorted), _p(tile_range), bg, W, H, _p(final_T),
+                                         _p(ncontrib), _p(g), _p(grec), stream)
+            launch("pxb_fused_backward", P, sh_degree, _p(pos), _p(sc), _p(rot), _p(sh), n_extra, with_depth, _p(intr),
+                                         _p(extr), _p(cc), W, H, S, _p(depth), _p(radius), _p(grec), _p(d_pos), _p(d_sc),
+                                         _p(d_rot), _p(d_op), _p(d_sh), _p(d_extra), _p(d_ndc), _p(d_cam), stream)
+        d_intr = d_cam[0:4].reshape(s_intr) if ctx.needs_input_grad[6] else None
+        d_extr = d_cam[4:16].reshape(s_extr) if ctx.needs_input_grad[7] else None
+        d_cc = d_cam[16:19].reshape(s_cc) if ctx.needs_input_grad[8] else None
+        return (d_pos, d_op.reshape(s_op), d_sc, d_rot, d_sh, d_extra, d_intr, d_extr, d_cc, d_ndc,
+                None, None, None, None, None, None)
+
+
+def fused_render(position, opacity, scaling, rotation, shs, intr, extr, cam_center, ndc, sh_degree, W, H, bg,
+                 with_depth=False, extra=None, nearest=0.2):
+    """(features[C,H,W], radii[P]) through the fused path; ``extr`` is the 3x4 [R|T]."""
+    return _FusedRender.apply(position, opacity, scaling, rotation, shs, extra, intr, extr, cam_center, ndc,
+                              sh_degree, W, H, bg, with_depth, nearest)
+
+
+@register_renderer
+class MsplatRender(BaseObject):
+    """Render Gaussian point clouds with the B200-native msplat path."""
+
+    @dataclass
+    class Config:
+        update_sh_iter: int = 1000
+        max_sh_degree: int = 3
+        render_depth: bool = False
+
+    cfg: Config
+
+    def setup(self, white_bg, device, **kwargs):
+        self.sh_degree = 0
+        self.device = device
+        super().setup(white_bg, device, **kwargs)
+        self.bg_color = 1.0 if white_bg else 0.0
+
+    # ------------------------------------------------------------------
+    def render_iter(self, height, width, extrinsic_matrix, intrinsic_params, camera_center, position, opacity,
+                    scaling, rotation, shs, **kwargs) -> dict:
+        """One view.  Extra per-Gaussian feature tensors ``[P,c]`` passed as keyword
+        arguments (e.g. ``normals``) are blended as additional channels and
+        returned under their keyword name (examples/supervise/renderer.py:25-102);
+        any other keyword is ignored, as in the reference."""
+        if not position.is_cuda:
+            raise RuntimeError("position must be a CUDA tensor")
+        P = position.shape[0]
+        extras = {k: v for k, v in kwargs.items()
+                  if isinstance(v, Tensor) and v.dim() == 2 and v.shape[0] == P and v.is_floating_point()}
+        extra = torch.cat(list(extras.values()), dim=-1) if extras else None
+        extr = extrinsic_matrix[:3, :]
+        intr = intrinsic_params.reshape(-1)[:4] if intrinsic_params.numel() != 4 else intrinsic_params
+        n_ch = 3 + int(self.cfg.render_depth) + (0 if extra is None else extra.shape[1])
+        ndc = torch.zeros(P, 2, dtype=torch.float32, device=position.device, requires_grad=True)
+        try:
+            ndc.retain_grad()
+        except Exception:
+            raise ValueError("ndc does not have grad")
+
+        fused_ok = (shs.dim() == 3 and shs.shape[1] == 16 and shs.shape[2] == 3 and self.sh_degree <= 3
+                    and n_ch <= ops.MAX_CH and P > 0)
+        if fused_ok:
+            feats, radius = fused_render(position, opacity, scaling, rotation, shs, intr, extr, camera_center, ndc,
+                                         self.sh_degree, width, height, self.bg_color, self.cfg.render_depth, extra)
+        else:
+            feats, radius = self._render_iter_ops(height, width, extr, intr, camera_center, position, opacity, scaling,
+                                                  rotation, shs, extra, ndc)
+        split, s = {}, 0
+        names = [("rgb", 3)] + ([("depth", 1)] if self.cfg.render_depth else []) + [(k, v.shape[1]) for k, v in extras.items()]
+        for k, c in names:
+            split[k] = feats[s:s + c]
+            s += c
+        return {"rendered_features_split": split, "uv_points": ndc, "visibility": radius > 0, "radii": radius}
+
+    def _render_iter_ops(self, height, width, extr, intr, camera_center, position, opacity, scaling, rotation, shs,
+                         extra, ndc):
+        """Operator-by-operator composition, the literal sequence of
+        pointrix/model/renderer/msplat.py:94-151 (used for SH layouts / channel
+        counts the fused kernels do not cover)."""
+        direction = position - camera_center.reshape(1, 3)
+        direction = direction / direction.norm(dim=1, keepdim=True)
+        sh_coeff = shs.permute(0, 2, 1)
+        sh_mask = torch.zeros_like(sh_coeff)
+        sh_mask[..., :(self.sh_degree + 1) ** 2] = 1.0
+        rgb = ops.compute_sh(sh_coeff * sh_mask, direction)
+        rgb = (rgb + 0.5).clamp(min=0.0)
+        uv, depth = ops.project_point(position, intr, extr, width, height, nearest=0.2)
+        visible = depth != 0
+        cov3d = ops.compute_cov3d(scaling, rotation, visible)
+        conic, radius, tiles = ops.ewa_project(position, cov3d, intr, extr, uv, width, height, visible)
+        ids, tile_range = ops.sort_gaussian(uv, depth, width, height, radius, tiles)
+        cols = [rgb] + ([depth] if self.cfg.render_depth else []) + ([extra] if extra is not None else [])
+        feats = ops.alpha_blending(uv, conic, opacity, torch.cat(cols, dim=-1), ids, tile_range, self.bg_color, width,
+                                   height, ndc)
+        return feats, radius
+
+    # ------------------------------------------------------------------
+    def render_batch(self, render_dict: dict) -> dict:
+        """Loop the views of a batch (pointrix/model/renderer/msplat.py:160-213): only
+        ``extrinsic_matrix`` and ``camera_center`` are sliced per view."""
+        rendered_features: Dict[str, list] = {}
+        uv_points, visibilitys, radii = [], [], []
+        batched = ("extrinsic_matrix", "camera_center")
+        for i in range(render_dict["extrinsic_matrix"].shape[0]):
+            it = {k: (v[i, ...] if k in batched else v) for k, v in render_dict.items()}
+            res = self.render_iter(**it)
+            for name, feat in res["rendered_features_split"].items():
+                rendered_features.setdefault(name, []).append(feat)
+            uv_points.append(res["uv_points"])
+            visibilitys.append(res["visibility"].unsqueeze(0))
+            radii.append(res["radii"].unsqueeze(0))
+        stacked = {k: torch.stack(v, dim=0) for k, v in rendered_features.items()}
+        return {**stacked, "uv_points": uv_points, "visibility": torch.cat(visibilitys).any(dim=0),
+                "radii": torch.cat(radii, 0).max(dim=0).values}
+
+    def update_sh_degree(self, step):
+        if step % self.cfg.update_sh_iter == 0:
+            if self.sh_degree < self.cfg.max_sh_degree:
+                self.sh_degree += 1
+
+    def load_state_dict(self, state_dict):
+        self.sh_degree = state_dict["sh_degree"]
+
+    def state_dict(self):
+        return {"sh_degree": self.sh_degree}
