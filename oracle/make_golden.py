@@ -1,0 +1,161 @@
+"""Golden-vector generator -- TEST INFRASTRUCTURE ONLY.
+
+Two sources, both the reference itself:
+
+  python oracle/make_golden.py --from-ref-tests
+      (this container, CPU) imports the reference's OWN in-test PyTorch oracles from
+      /root/reference/msplat/test/test_*.py (project_point_torch_impl,
+      compute_cov3d_torch_impl, ewa_project_torch_impl, eval_sh_bases,
+      alpha_blending_torch_impl) with the reference's seeds / shapes, runs them on CPU
+      and stores inputs + outputs (+ autograd gradients) in
+      tests/golden/ref_test_oracles.npz.  Nothing is copied: the functions are imported
+      where they lie, `msplat` is stubbed and `.cuda()` is made a no-op.
+
+  python oracle/make_golden.py --from-ref-gpu [out.npz]
+      (GPU box) runs the compiled unmodified reference CUDA (oracle/_ref) on a small
+      seeded scene through its own op order and stores every intermediate and gradient
+      -> tests/golden/ref_gpu_small.npz (written to gpurun_out/ on the box and copied).
+"""
+from __future__ import annotations
+
+import importlib.util
+import math
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, ROOT)
+REF_TESTS = "/root/reference/msplat/test"
+
+
+def _import_ref_test(name):
+    sys.modules.setdefault("msplat", types.ModuleType("msplat"))
+    import scipy.special as sp
+
+    if not hasattr(sp, "sph_harm"):  # removed in recent scipy; the test only needs the name at import
+        sp.sph_harm = lambda m, n, theta, phi: sp.sph_harm_y(n, m, phi, theta)
+    spec = importlib.util.spec_from_file_location("ref_" + name, os.path.join(REF_TESTS, name + ".py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def from_ref_tests(out_path):
+    torch.Tensor.cuda = lambda self, *a, **k: self  # the helpers hard-code .cuda()
+    G = {}
+    # ---- project_point (test_project_points.py:55-77 inputs)
+    m = _import_ref_test("test_project_points")
+    torch.manual_seed(123)
+    W, H, N = 1600, 1200, 1000
+    intr = torch.tensor([2892.33, 2883.18, 823.205, 619.071])
+    extr = torch.tensor([[0.970263, 0.00747983, 0.241939, -191.02], [-0.0147429, 0.999493, 0.0282234, 3.2883],
+                         [-0.241605, -0.030951, 0.969881, 22.5401]])
+    xyz = torch.rand(N, 3)
+    xyz[:, 0] *= 500; xyz[:, 1] *= 500; xyz[:, 2] = xyz[:, 2] * 400 + 400
+    x1 = xyz.clone().requires_grad_()
+    uv, depth = m.project_point_torch_impl(x1, intr, extr, W, H)
+    (uv.sum() + depth.sum()).backward()
+    G.update(proj_xyz=xyz, proj_intr=intr, proj_extr=extr, proj_WH=torch.tensor([W, H]), proj_uv=uv.detach(),
+             proj_depth=depth.detach(), proj_dxyz=x1.grad)
+    # ---- compute_cov3d (test_compute_cov3d.py:38-47)
+    m = _import_ref_test("test_compute_cov3d")
+    torch.manual_seed(7)
+    N = 2000
+    s = torch.rand(N, 3)
+    q = torch.randn(N, 4); q = q / q.norm(dim=-1, keepdim=True)
+    s1, q1 = s.clone().requires_grad_(), q.clone().requires_grad_()
+    cov = m.compute_cov3d_torch_impl(s1, q1)
+    cov.sum().backward()
+    G.update(cov_scales=s, cov_quats=q, cov_out=cov.detach(), cov_ds=s1.grad, cov_dq=q1.grad)
+    # ---- ewa_project (test_ewa_project.py:140-161)
+    m = _import_ref_test("test_ewa_project")
+    torch.manual_seed(123)
+    N, W, H = 4000, 800, 800
+    intr = torch.tensor([1111.0, 1111.0, H / 2, W / 2 / 2])
+    extr = torch.tensor([[6.1182e-01, 7.9099e-01, 1.3906e-14, 1.1327e-09], [7.9096e-01, -6.1180e-01, -8.5126e-03, 1.0458e-09],
+                         [-6.7348e-03, 5.2093e-03, -9.9996e-01, 4.0311e+00]])
+    xyz = torch.randn(N, 3) * 2.6 - 1.3
+    sc = torch.rand(N, 3) + 1
+    qq = torch.rand(N, 4); qq = qq / qq.norm(dim=-1, keepdim=True)
+    from oracle import msplat_oracle as O
+
+    cov3d = O.compute_cov3d(sc, qq)
+    uv, depth = O.project_point(xyz, intr, extr, W, H, nearest=0.2)
+    vis = (depth != 0).reshape(-1)
+    m.uv = uv  # the helper reads a module-global `uv` for its device
+    x1, c1, i1, e1 = xyz.clone().requires_grad_(), cov3d.clone().requires_grad_(), intr.clone().requires_grad_(), extr.clone().requires_grad_()
+    conic, radius, tiles = m.ewa_project_torch_impl(x1, c1, i1, e1, uv, W, H, vis)
+    conic.sum().backward()
+    G.update(ewa_xyz=xyz, ewa_cov3d=cov3d, ewa_intr=intr, ewa_extr=extr, ewa_uv=uv, ewa_vis=vis, ewa_WH=torch.tensor([W, H]),
+             ewa_conic=conic.detach(), ewa_radius=radius, ewa_tiles=tiles, ewa_dxyz=x1.grad, ewa_dcov3d=c1.grad,
+             ewa_dintr=i1.grad, ewa_dextr=e1.grad)
+    # ---- SH bases, degrees 0..10 (test_compute_sh.py:162-325)
+    m = _import_ref_test("test_compute_sh")
+    torch.manual_seed(123)
+    d = torch.randn(64, 3, dtype=torch.float64); d = d / d.norm(dim=1, keepdim=True)
+    G["sh_dirs"] = d
+    for deg in range(11):
+        G[f"sh_bases_{deg}"] = m.eval_sh_bases((deg + 1) ** 2, d)
+    # ---- alpha blending, per-pixel loop oracle (test_alpha_blending.py:6-63,112-134: 32x16, N=20, C=33, bg=1)
+    m = _import_ref_test("test_alpha_blending")
+    torch.manual_seed(121)
+    w, h, bg, N = 32, 16, 1, 20
+    uv = torch.rand(N, 2); uv[:, 0] *= w; uv[:, 1] *= h
+    A = torch.randn(N, 2, 2); cv = torch.bmm(A, A.transpose(1, 2))
+    conic = torch.stack([cv[:, 0, 0], cv[:, 0, 1], cv[:, 1, 1]], -1)
+    depth = torch.rand(N, 1) * 5
+    radius = (torch.rand(N, 1) * 5).int()
+    tiles = m.get_tiles(uv, radius.squeeze(-1), w, h)
+    opacity = torch.rand(N, 1)
+    feature = torch.rand(N, 33)
+    ids, tr = O.sort_gaussian(uv, depth, w, h, radius, tiles)
+    u1, c1, o1, f1 = uv.clone().requires_grad_(), conic.clone().requires_grad_(), opacity.clone().requires_grad_(), feature.clone().requires_grad_()
+    img = m.alpha_blending_torch_impl(u1, c1, o1, f1, ids, tr, bg, w, h)
+    img.sum().backward()
+    G.update(ab_uv=uv, ab_conic=conic, ab_depth=depth, ab_radius=radius, ab_tiles=tiles, ab_opacity=opacity, ab_feature=feature,
+             ab_ids=ids, ab_tr=tr, ab_img=img.detach(), ab_duv=u1.grad, ab_dconic=c1.grad, ab_dop=o1.grad, ab_dfeat=f1.grad)
+    np.savez_compressed(out_path, **{k: v.detach().cpu().numpy() for k, v in G.items()})
+    print("wrote", out_path, {k: tuple(v.shape) for k, v in G.items()})
+
+
+def from_ref_gpu(out_path):
+    from oracle import ref_driver
+    from pointrix_b200 import scene
+
+    assert ref_driver.available(), "needs oracle/_ref and a GPU"
+    P, W, H = 3000, 208, 120
+    c, sc, cams = scene.make_config("cfg1", P=P, views=1)
+    cams = scene.make_cameras(1, W, H, seed=1)
+    scd = {k: v.cuda() for k, v in sc.items()}
+    E, intr, cc = cams["extrinsic_matrix"][0].cuda(), cams["intrinsic_params"].cuda(), cams["camera_center"][0].cuda()
+    g = torch.Generator().manual_seed(11)
+    extra = torch.randn(P, 5, generator=g)
+    G = dict(P=torch.tensor(P), W=torch.tensor(W), H=torch.tensor(H), E=E, intr=intr, cc=cc, extra=extra, **sc)
+    for tag, deg, rd, ex in (("a", 3, False, None), ("b", 1, True, extra.cuda())):
+        f = ref_driver.render_forward(H, W, E, intr, cc, **scd, sh_degree=deg, render_depth=rd, extra=ex)
+        dimg = torch.randn(f["img"].shape, generator=g).cuda()
+        b = ref_driver.render_backward(f, dimg, scd["position"], scd["opacity"], scd["scaling"], scd["rotation"], scd["shs"], cc,
+                                       sh_degree=deg, render_depth=rd, n_extra=0 if ex is None else ex.shape[1], camera_grads=True)
+        for k in ("uv", "depth", "cov3d", "conic", "radius", "tiles", "idx_sorted", "tile_range", "keys", "rgb", "img", "final_T", "ncontrib"):
+            G[f"{tag}_{k}"] = f[k]
+        G[f"{tag}_dimg"] = dimg
+        for k, v in b.items():
+            G[f"{tag}_g_{k}"] = v
+    np.savez_compressed(out_path, **{k: v.detach().cpu().numpy() for k, v in G.items()})
+    print("wrote", out_path)
+
+
+if __name__ == "__main__":
+    if "--from-ref-tests" in sys.argv:
+        from_ref_tests(os.path.join(ROOT, "tests", "golden", "ref_test_oracles.npz"))
+    elif "--from-ref-gpu" in sys.argv:
+        out = sys.argv[-1] if sys.argv[-1].endswith(".npz") else os.path.join(ROOT, "gpurun_out", "ref_gpu_small.npz")
+        os.makedirs(os.path.dirname(out), exist_ok=True)
+        from_ref_gpu(out)
+    else:
+        print(__doc__)

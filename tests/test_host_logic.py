@@ -1,0 +1,119 @@
+"""Host-side logic of the plugin boundary (no GPU): registry, config, SH warm-up, state dict,
+feature combine/split, argument checking, view sharding and the gloo all-reduce step."""
+import os
+
+import pytest
+import torch
+
+import pointrix_b200 as pb
+from pointrix_b200 import parallel
+
+
+def _renderer(**cfg):
+    return pb.parse_renderer({"name": "MsplatRender", **cfg}, white_bg=True, device="cuda:0")
+
+
+def test_registry_and_config():
+    assert "MsplatRender" in pb.RENDERER_REGISTRY
+    r = _renderer()
+    assert (r.cfg.update_sh_iter, r.cfg.max_sh_degree, r.cfg.render_depth) == (1000, 3, False)
+    assert r.sh_degree == 0 and r.bg_color == 1.0
+    assert pb.parse_renderer({"name": "MsplatRender"}, white_bg=False, device="cuda:0").bg_color == 0.0
+    with pytest.raises(KeyError):
+        _renderer(not_a_field=1)
+    with pytest.raises(KeyError):
+        pb.parse_renderer({"name": "NoSuchRender"}, white_bg=True, device="cuda:0")
+
+
+def test_sh_warmup_and_state_dict():
+    """pointrix/model/renderer/msplat.py:215-248"""
+    r = _renderer(update_sh_iter=10, max_sh_degree=2)
+    seen = []
+    for step in range(0, 45):
+        r.update_sh_degree(step)
+        seen.append(r.sh_degree)
+    assert seen[0] == 1 and seen[9] == 1 and seen[10] == 2 and seen[-1] == 2  # +1 at 0, 10; capped at max
+    sd = r.state_dict()
+    assert sd == {"sh_degree": 2}
+    r2 = _renderer()
+    r2.load_state_dict(sd)
+    assert r2.sh_degree == 2
+
+
+def test_render_features_combine_split():
+    a, b = torch.rand(5, 3), torch.rand(5, 1)
+    rf = pb.RenderFeatures(rgb=a, depth=b)
+    comb = rf.combine()
+    assert comb.shape == (5, 4) and torch.equal(comb[:, :3], a)
+    img = torch.rand(4, 6, 7)
+    sp = rf.split(img)
+    assert list(sp) == ["rgb", "depth"] and sp["rgb"].shape == (3, 6, 7) and torch.equal(sp["depth"], img[3:4])
+
+
+def test_cpu_tensors_are_rejected():
+    """the reference's CHECK_INPUT: '<x> must be a CUDA tensor' (msplat/msplat/include/utils.h:9-10)"""
+    with pytest.raises(RuntimeError, match="must be a CUDA tensor"):
+        pb.project_point(torch.zeros(4, 3), torch.zeros(4), torch.zeros(3, 4), 8, 8)
+    with pytest.raises(RuntimeError, match="must be a CUDA tensor"):
+        pb.compute_sh(torch.zeros(4, 3, 16), torch.zeros(4, 3))
+    r = _renderer()
+    with pytest.raises(RuntimeError, match="must be a CUDA tensor"):
+        r.render_iter(8, 8, torch.eye(4), torch.zeros(4), torch.zeros(3), torch.zeros(4, 3), torch.zeros(4, 1),
+                      torch.zeros(4, 3), torch.zeros(4, 4), torch.zeros(4, 16, 3))
+
+
+def test_no_oracle_on_the_product_path():
+    """The package never imports oracle/ (CPU restatement) -- there is no fallback."""
+    import pathlib
+
+    root = pathlib.Path(pb.__file__).parent
+    for f in root.rglob("*.py"):
+        txt = f.read_text()
+        assert "import oracle" not in txt and "from oracle" not in txt, f
+
+
+def test_shard_views():
+    for world in (1, 2, 4, 8):
+        for step in (0, 3):
+            got = sorted(v for r in range(world) for v in parallel.shard_views(16, r, world, step))
+            assert got == list(range(16))
+    assert parallel.shard_views(16, 1, 4) == [1, 5, 9, 13]
+
+
+def _worker(rank, world, port, q):
+    import torch.distributed as dist
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    g = torch.Generator().manual_seed(100 + rank)
+    grads = [torch.randn(50, 3, generator=g), torch.randn(50, 16, 3, generator=g)]
+    ndc = torch.randn(50, 2, generator=g)
+    radii = torch.randint(0, 9, (50,), generator=g, dtype=torch.int32)
+    keep = [x.clone() for x in grads] + [ndc.clone(), radii.clone()]
+    vis = parallel.allreduce_step(grads, ndc, radii, world)
+    q.put((rank, [x.numpy() for x in keep], [x.numpy() for x in grads] + [ndc.numpy(), radii.numpy(), vis.numpy()]))
+    dist.destroy_process_group()
+
+
+def test_allreduce_step_gloo_world2():
+    """world_size ranks x 1 view == one reference batch of world_size views: parameter grads are
+    averaged, ndc grads summed, radii max-reduced, visibility = any."""
+    import numpy as np
+    import torch.multiprocessing as mp
+
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000)
+    ps = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in ps:
+        p.start()
+    res = sorted([q.get(timeout=120) for _ in ps], key=lambda t: t[0])
+    for p in ps:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    (_, k0, o0), (_, k1, o1) = res
+    for i in range(2):
+        np.testing.assert_allclose(o0[i], (k0[i] + k1[i]) / 2, rtol=1e-6, atol=1e-6)
+        np.testing.assert_allclose(o1[i], o0[i])
+    np.testing.assert_allclose(o0[2], k0[2] + k1[2], rtol=1e-6, atol=1e-6)
+    assert (o0[3] == np.maximum(k0[3], k1[3])).all() and (o0[4] == (o0[3] > 0)).all()
