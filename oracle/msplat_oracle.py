@@ -389,7 +389,10 @@ def alpha_blending(
         cn = conic[g]  # [nt,n,3]
         power = -0.5 * (cn[:, None, :, 0] * dx * dx + cn[:, None, :, 2] * dy * dy) - cn[:, None, :, 1] * dx * dy
         G = torch.exp(power)
-        alpha = torch.clamp(opacity.reshape(-1)[g][:, None, :] * G, max=0.99)
+        alpha_raw = opacity.reshape(-1)[g][:, None, :] * G
+        # min(0.99, .) is applied to the value only: the reference backward differentiates
+        # op*G as if unclamped (alpha_blending.cu:200-201,228 -- dL_dG = opac * dL_dalpha)
+        alpha = alpha_raw + (torch.clamp(alpha_raw, max=0.99) - alpha_raw).detach()
         valid = in_list[:, None, :] & ~(power > 0) & ~(alpha < 1.0 / 255.0)
         a_eff = torch.where(valid, alpha, torch.zeros_like(alpha))
         T_incl = torch.cumprod(1.0 - a_eff, dim=-1)
