@@ -86,6 +86,13 @@ int pxb_sort_gaussian(int P, long long N, const float* uv, int uv_stride, const 
                       const int* tiles, const int* offsets_incl, int W, int H, int* idx_sorted, int* tile_range,
                       long long* keys_sorted_out, void* ws, size_t ws_bytes, void* stream);
 
+/* Sync-free variant used by the fused plugin path: grids/buffers sized for N_cap, the kernels read the
+ * actual intersection count from *total_dev and process min(*total_dev, N_cap) entries; the caller
+ * verifies *total_dev <= N_cap afterwards (asynchronously) and re-runs with more capacity otherwise. */
+int pxb_sort_gaussian_dev(int P, long long N_cap, const int* total_dev, const float* uv, int uv_stride,
+                          const float* depth, const int* radius, const int* tiles, const int* offsets_incl, int W,
+                          int H, int* idx_sorted, int* tile_range, void* ws, size_t ws_bytes, void* stream);
+
 /* ---- alpha blending: replaces alphaBlendingForward/Backward
  *      (include/alpha_blending.h, src/alpha_blending.cu:248-572) ---- */
 int pxb_record_stride(int C); /* S for C <= PXB_MAX_CHANNELS_PER_PASS channels, else -1 */

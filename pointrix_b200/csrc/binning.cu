@@ -21,7 +21,8 @@ namespace pxb {
 constexpr int kScanThreads = 256;
 constexpr int kScanItems = 8;
 constexpr int kScanTile = kScanThreads * kScanItems;
-constexpr unsigned long long kFlagAgg = 1ull << 32, kFlagPrefix = 2ull << 32;
+#define kFlagAgg (1ull << 32)
+#define kFlagPrefix (2ull << 32)
 
 __global__ void __launch_bounds__(kScanThreads)
 scan_kernel(int P, const int* __restrict__ in, int* __restrict__ out, int* __restrict__ total,
@@ -56,26 +57,33 @@ scan_kernel(int P, const int* __restrict__ in, int* __restrict__ out, int* __res
         if (w < warp) warp_off += s;
         block_sum += s;
     }
-    if (threadIdx.x == 0) {
+    if (warp == 0) {
+        // warp-parallel decoupled look-back: 32 predecessors per probe
         volatile unsigned long long* st = status;
+        if (lane == 0) st[tile] = (tile == 0 ? kFlagPrefix : kFlagAgg) | (unsigned int)block_sum;
         int excl = 0;
-        if (tile == 0) {
-            st[0] = kFlagPrefix | (unsigned int)block_sum;
-        } else {
-            st[tile] = kFlagAgg | (unsigned int)block_sum;
-            int t = tile - 1;
-            while (true) {
-                const unsigned long long s = st[t];
-                const unsigned int flag = (unsigned int)(s >> 32);
-                if (flag == 0) continue;
-                excl += (int)(unsigned int)s;
-                if (flag == 2) break;
-                t--;
-            }
-            st[tile] = kFlagPrefix | (unsigned int)(excl + block_sum);
+        int t_base = tile - 1;
+        while (t_base >= 0) {
+            const int idx = t_base - lane;
+            const unsigned long long sv = (idx >= 0) ? st[idx] : kFlagPrefix;
+            const unsigned int flag = (unsigned int)(sv >> 32);
+            const unsigned int zero = __ballot_sync(0xffffffffu, flag == 0);
+            const unsigned int pref = __ballot_sync(0xffffffffu, flag == 2);
+            const int first = pref ? (__ffs(pref) - 1) : 32;          // nearest tile holding an inclusive prefix
+            const unsigned int need = (first < 32) ? ((2u << first) - 1u) : 0xffffffffu;
+            if (zero & need) continue;                                 // some needed predecessor not published yet
+            int v_ = (lane <= first) ? (int)(unsigned int)sv : 0;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v_ += __shfl_xor_sync(0xffffffffu, v_, o);
+            excl += v_;
+            if (first < 32) break;
+            t_base -= 32;
         }
-        s_excl = excl;
-        if ((tile + 1) * kScanTile >= P) *total = excl + block_sum;
+        if (lane == 0) {
+            if (tile > 0) st[tile] = kFlagPrefix | (unsigned int)(excl + block_sum);
+            s_excl = excl;
+            if ((tile + 1) * kScanTile >= P) *total = excl + block_sum;
+        }
     }
     __syncthreads();
     int run = s_excl + warp_off + (incl - sum);
@@ -94,8 +102,9 @@ constexpr int kEmitThreads = 256;
 __global__ void __launch_bounds__(kEmitThreads)
 emit_keys_kernel(int P, const float* __restrict__ uv, int uv_stride, const float* __restrict__ depth,
                  const int* __restrict__ radius, const int* __restrict__ tiles, const int* __restrict__ offs_incl,
-                 int gx, int gy, long long N, unsigned long long* __restrict__ keys,
-                 unsigned int* __restrict__ vals) {
+                 int gx, int gy, long long N_cap, const int* __restrict__ n_dev,
+                 unsigned long long* __restrict__ keys, unsigned int* __restrict__ vals) {
+    const long long N = n_dev ? min((long long)*n_dev, N_cap) : N_cap;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
     int x0 = 0, y0 = 0, w = 0, cnt = 0, off = 0;
@@ -159,11 +168,15 @@ constexpr int kRsItems = 16;
 constexpr int kRsTile = kRsThreads * kRsItems;  // 4096 pairs per block
 constexpr int kRadix = 256;
 constexpr int kMaxPasses = 8;
-constexpr unsigned int kStAgg = 1u << 30, kStPrefix = 2u << 30, kStMask = (1u << 30) - 1u;
+#define kStAgg (1u << 30)
+#define kStPrefix (2u << 30)
+#define kStMask ((1u << 30) - 1u)
 
 __global__ void __launch_bounds__(kRsThreads)
-rs_histogram_kernel(const unsigned long long* __restrict__ keys, int N, int passes, unsigned int* __restrict__ hist) {
+rs_histogram_kernel(const unsigned long long* __restrict__ keys, int N_cap, const int* __restrict__ n_dev, int passes,
+                    unsigned int* __restrict__ hist) {
     __shared__ unsigned int h[kMaxPasses][kRadix];
+    const int N = n_dev ? min(*n_dev, N_cap) : N_cap;
     for (int k = threadIdx.x; k < kMaxPasses * kRadix; k += blockDim.x) (&h[0][0])[k] = 0;
     __syncthreads();
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (long long)gridDim.x * blockDim.x) {
@@ -208,9 +221,10 @@ struct RsSmem {
 
 __global__ void __launch_bounds__(kRsThreads)
 rs_onesweep_kernel(const unsigned long long* __restrict__ keys_in, const unsigned int* __restrict__ vals_in,
-                   unsigned long long* __restrict__ keys_out, unsigned int* __restrict__ vals_out, int N, int shift,
-                   const unsigned int* __restrict__ bin_base /*[256] exclusive*/, unsigned int* status,
-                   unsigned int* ticket) {
+                   unsigned long long* __restrict__ keys_out, unsigned int* __restrict__ vals_out, int N_cap,
+                   const int* __restrict__ n_dev, int shift, const unsigned int* __restrict__ bin_base /*[256] exclusive*/,
+                   unsigned int* status, unsigned int* ticket) {
+    const int N = n_dev ? min(*n_dev, N_cap) : N_cap;
     extern __shared__ __align__(16) unsigned char rs_raw[];
     RsSmem& sm = *reinterpret_cast<RsSmem*>(rs_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -218,6 +232,7 @@ rs_onesweep_kernel(const unsigned long long* __restrict__ keys_in, const unsigne
     for (int k = tid; k < (kRsThreads / 32) * kRadix; k += kRsThreads) (&sm.warp_hist[0][0])[k] = 0;
     __syncthreads();
     const int tile = sm.tile;
+    if ((long long)tile * kRsTile >= N) return;  // capacity-sized grid: surplus CTAs leave
     const long long tile_base = (long long)tile * kRsTile;
     const int tile_n = (int)min((long long)kRsTile, (long long)N - tile_base);
 
@@ -237,26 +252,39 @@ rs_onesweep_kernel(const unsigned long long* __restrict__ keys_in, const unsigne
             val[k] = 0;
         }
     }
-    // warp-level stable ranking with match.any; counters private to the warp
+    // warp-level stable ranking; counters private to the warp.  The peer masks of all items are
+    // computed first (independent work that pipelines); only the short leader read-modify-write
+    // of the warp-private counter is serial per item.
     const unsigned int lt_mask = (1u << lane) - 1u;
     unsigned int* wh = sm.warp_hist[warp];
+    unsigned int peers[kRsItems];
 #pragma unroll
     for (int k = 0; k < kRsItems; k++) {
         const bool valid = (wbase + k * 32) < tile_n;
         const unsigned int d = (unsigned int)(key[k] >> shift) & 255u;
         const unsigned int vmask = __ballot_sync(0xffffffffu, valid);
-        unsigned int peers = __match_any_sync(0xffffffffu, d) & vmask;
+        // lanes holding the same digit: eight ballots (MATCH.ANY proved to be the pass's bottleneck:
+        // ~40 % of the stall samples sat on its consumer in the first profile)
+        unsigned int m = vmask;
+#pragma unroll
+        for (int b = 0; b < 8; b++) {
+            const bool bit = (d >> b) & 1u;
+            const unsigned int bal = __ballot_sync(0xffffffffu, bit);
+            m &= bit ? bal : ~bal;
+        }
+        peers[k] = valid ? m : 0u;
+    }
+#pragma unroll
+    for (int k = 0; k < kRsItems; k++) {
+        const unsigned int d = (unsigned int)(key[k] >> shift) & 255u;
         unsigned int old = 0;
-        int leader = 0;
-        if (valid) {
-            leader = __ffs(peers) - 1;
-            if (lane == leader) {
-                old = wh[d];
-                wh[d] = old + __popc(peers);
-            }
+        const int leader = peers[k] ? (__ffs(peers[k]) - 1) : 0;
+        if (peers[k] && lane == leader) {
+            old = wh[d];
+            wh[d] = old + __popc(peers[k]);
         }
         old = __shfl_sync(0xffffffffu, old, leader);
-        rank[k] = old + __popc(peers & lt_mask);
+        rank[k] = old + __popc(peers[k] & lt_mask);
         __syncwarp();
     }
     __syncthreads();
@@ -286,18 +314,28 @@ rs_onesweep_kernel(const unsigned long long* __restrict__ keys_in, const unsigne
         for (int w = 0; w < warp; w++) off += sm.warp_sums[w];
         sm.digit_start[tid] = off + incl - count;
     }
-    // decoupled look-back: digits are independent, one thread per digit
+    // decoupled look-back: digits are independent, one thread per digit.  Eight predecessors are
+    // probed per round trip (independent loads) so that the first wave, where every resident CTA
+    // still holds only its aggregate, is walked 8 tiles per L2 latency instead of one.
     {
         unsigned int excl = 0;
         if (tile > 0) {
+            const volatile unsigned int* st = status + tid;
             int t = tile - 1;
-            while (true) {
-                const unsigned int s = *((volatile unsigned int*)(status + (size_t)t * kRadix + tid));
-                const unsigned int flag = s >> 30;
-                if (flag == 0) continue;
-                excl += s & kStMask;
-                if (flag == 2) break;
-                t--;
+            bool done_lb = false;
+            while (!done_lb) {
+                unsigned int sv[8];
+#pragma unroll
+                for (int u = 0; u < 8; u++) sv[u] = (t - u >= 0) ? st[(size_t)(t - u) * kRadix] : kStPrefix;
+#pragma unroll
+                for (int u = 0; u < 8; u++) {
+                    if (done_lb) break;
+                    const unsigned int flag = sv[u] >> 30;
+                    if (flag == 0) break;  // not published yet: re-probe from this tile
+                    excl += sv[u] & kStMask;
+                    t--;
+                    if (flag == 2) done_lb = true;
+                }
             }
             *((volatile unsigned int*)(status + (size_t)tile * kRadix + tid)) = kStPrefix | (excl + count);
         }
@@ -332,8 +370,10 @@ rs_onesweep_kernel(const unsigned long long* __restrict__ keys_in, const unsigne
 // ---------------------------------------------------------------------------
 // 4. tile ranges (sort_gaussian.cu:45-71)
 // ---------------------------------------------------------------------------
-__global__ void tile_range_kernel(int N, const unsigned long long* __restrict__ keys_sorted, int num_tiles,
+__global__ void tile_range_kernel(int N_cap, const int* __restrict__ n_dev,
+                                  const unsigned long long* __restrict__ keys_sorted, int num_tiles,
                                   int2* __restrict__ tile_range) {
+    const int N = n_dev ? min(*n_dev, N_cap) : N_cap;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N) return;
     const int cur = (int)(keys_sorted[i] >> 32);
@@ -419,11 +459,9 @@ int pxb_tile_scan(int P, const int* tiles, int* offsets_incl, int* total_dev, vo
     return (int)cudaGetLastError();
 }
 
-// keys + sort + ranges.  N = offsets_incl[P-1] (the caller has read it back).
-int pxb_sort_gaussian(int P, long long N, const float* uv, int uv_stride, const float* depth, const int* radius,
-                      const int* tiles, const int* offsets_incl, int W, int H, int* idx_sorted, int* tile_range,
-                      long long* keys_sorted_out /*nullable, [N]*/, void* ws, size_t ws_bytes, void* stream) {
-    cudaStream_t s = (cudaStream_t)stream;
+static int sort_impl(int P, long long N, const int* n_dev, const float* uv, int uv_stride, const float* depth,
+                     const int* radius, const int* tiles, const int* offsets_incl, int W, int H, int* idx_sorted,
+                     int* tile_range, long long* keys_sorted_out, void* ws, size_t ws_bytes, cudaStream_t s) {
     const int gx = (W + PXB_TILE - 1) / PXB_TILE, gy = (H + PXB_TILE - 1) / PXB_TILE;
     const int num_tiles = gx * gy;
     PXB_CUDA_OK(cudaMemsetAsync(tile_range, 0, (size_t)num_tiles * 2 * sizeof(int), s));
@@ -440,9 +478,9 @@ int pxb_sort_gaussian(int P, long long N, const float* uv, int uv_stride, const 
     unsigned int* vcur = (passes % 2 == 0) ? (unsigned int*)idx_sorted : b.vals_tmp;
     unsigned int* valt = (passes % 2 == 0) ? b.vals_tmp : (unsigned int*)idx_sorted;
     emit_keys_kernel<<<(P + kEmitThreads - 1) / kEmitThreads, kEmitThreads, 0, s>>>(
-        P, uv, uv_stride, depth, radius, tiles, offsets_incl, gx, gy, N, kcur, vcur);
+        P, uv, uv_stride, depth, radius, tiles, offsets_incl, gx, gy, N, n_dev, kcur, vcur);
     const int hist_blocks = (int)min((long long)(148 * 8), (N + kRsThreads * 8 - 1) / (kRsThreads * 8));
-    rs_histogram_kernel<<<hist_blocks, kRsThreads, 0, s>>>(kcur, (int)N, passes, b.hist);
+    rs_histogram_kernel<<<hist_blocks, kRsThreads, 0, s>>>(kcur, (int)N, n_dev, passes, b.hist);
     rs_scan_hist_kernel<<<passes, kRadix, 0, s>>>(b.hist);
     static bool attr_set = false;
     if (!attr_set) {
@@ -451,15 +489,34 @@ int pxb_sort_gaussian(int P, long long N, const float* uv, int uv_stride, const 
     }
     for (int p = 0; p < passes; p++) {
         rs_onesweep_kernel<<<rs_tiles, kRsThreads, sizeof(RsSmem), s>>>(
-            kcur, vcur, kalt, valt, (int)N, 8 * p, b.hist + p * kRadix,
+            kcur, vcur, kalt, valt, (int)N, n_dev, 8 * p, b.hist + p * kRadix,
             b.rs_status + (size_t)p * (rs_tiles + 1) * kRadix, b.rs_ticket + p);
         unsigned long long* tk = kcur; kcur = kalt; kalt = tk;
         unsigned int* tv = vcur; vcur = valt; valt = tv;
     }
-    tile_range_kernel<<<(int)((N + 255) / 256), 256, 0, s>>>((int)N, kcur, num_tiles, (int2*)tile_range);
+    tile_range_kernel<<<(int)((N + 255) / 256), 256, 0, s>>>((int)N, n_dev, kcur, num_tiles, (int2*)tile_range);
     if (keys_sorted_out)
         PXB_CUDA_OK(cudaMemcpyAsync(keys_sorted_out, kcur, (size_t)N * 8, cudaMemcpyDeviceToDevice, s));
     return (int)cudaGetLastError();
+}
+
+// keys + sort + ranges.  N = offsets_incl[P-1] (the caller has read it back).
+int pxb_sort_gaussian(int P, long long N, const float* uv, int uv_stride, const float* depth, const int* radius,
+                      const int* tiles, const int* offsets_incl, int W, int H, int* idx_sorted, int* tile_range,
+                      long long* keys_sorted_out /*nullable, [N]*/, void* ws, size_t ws_bytes, void* stream) {
+    return sort_impl(P, N, nullptr, uv, uv_stride, depth, radius, tiles, offsets_incl, W, H, idx_sorted, tile_range,
+                     keys_sorted_out, ws, ws_bytes, (cudaStream_t)stream);
+}
+
+// Same, without a host round trip: buffers and grids are sized for N_cap, the kernels read the
+// actual count from *total_dev (written by pxb_tile_scan) and work on min(*total_dev, N_cap).
+// The caller checks *total_dev <= N_cap later (and re-runs with a larger capacity if not).
+int pxb_sort_gaussian_dev(int P, long long N_cap, const int* total_dev, const float* uv, int uv_stride,
+                          const float* depth, const int* radius, const int* tiles, const int* offsets_incl, int W,
+                          int H, int* idx_sorted, int* tile_range, void* ws, size_t ws_bytes, void* stream) {
+    if (total_dev == nullptr) return PXB_ERR_BAD_ARG;
+    return sort_impl(P, N_cap, total_dev, uv, uv_stride, depth, radius, tiles, offsets_incl, W, H, idx_sorted,
+                     tile_range, nullptr, ws, ws_bytes, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -1,6 +1,6 @@
 """Build libpointrix_b200.so in-tree with nvcc for sm_100a (no torch involved).
 
-    python -m pointrix_b200.csrc.build [--force] [--verbose]
+    python pointrix_b200/csrc/build.py [--force] [--verbose]
 
 The library has a plain C ABI (include/pointrix_b200.h) and links cudart
 statically, so it depends on nothing but the CUDA driver.

@@ -217,6 +217,59 @@ def _bin(uv_like: Tensor, uv_stride: int, depth: Tensor, radius: Tensor, tiles: 
     return idx_sorted, tile_range
 
 
+# capacity of the sync-free binning per (device, P, W, H): learnt from the previous views
+_CAPACITY = {}
+_PINNED = {}
+
+
+def _bin_nosync(uv_like: Tensor, uv_stride: int, depth: Tensor, radius: Tensor, tiles: Tensor, W: int, H: int):
+    """Binning without a host round trip on the critical path (fused plugin path).
+
+    Buffers and grids are sized for a capacity learnt from earlier views; the kernels read the
+    actual intersection count on the device.  Returns ``(idx_sorted[cap], tile_range, check)``
+    where ``check()`` -- to be called once the rest of the forward has been queued -- waits for the
+    count (copied to pinned memory right after the scan), and returns None if it fitted or the
+    exact count if the capacity was exceeded (the caller then re-bins and re-blends; rare)."""
+    dev = depth.device
+    P = radius.numel()
+    key = (dev.index, P, int(W), int(H))
+    cap = _CAPACITY.get(key)
+    if cap is None or P == 0:
+        idx_sorted, tile_range = _bin(uv_like, uv_stride, depth, radius, tiles, W, H)
+        _CAPACITY[key] = int(idx_sorted.numel() * 1.25) + 65536
+        return idx_sorted, tile_range, None
+    n_tiles = ((W + TILE - 1) // TILE) * ((H + TILE - 1) // TILE)
+    tile_range = torch.empty(n_tiles, 2, dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        stream = _stream(dev)
+        offsets = torch.empty(P, dtype=torch.int32, device=dev)
+        total = torch.empty(1, dtype=torch.int32, device=dev)
+        ws_bytes = lib.pxb_binning_workspace_bytes(P, cap, int(W), int(H))
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        launch("pxb_tile_scan", P, _p(tiles), _p(offsets), _p(total), _p(ws), ws_bytes, stream)
+        n_host = _PINNED.get(dev.index)
+        if n_host is None:
+            n_host = _PINNED[dev.index] = torch.zeros(1, dtype=torch.int32).pin_memory()
+        n_host.copy_(total, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        idx_sorted = torch.empty(cap, dtype=torch.int32, device=dev)
+        launch("pxb_sort_gaussian_dev", P, cap, _p(total), _p(uv_like), uv_stride, _p(depth), _p(radius), _p(tiles),
+               _p(offsets), int(W), int(H), _p(idx_sorted), _p(tile_range), _p(ws), ws_bytes, stream)
+
+    def check():
+        ev.synchronize()
+        n = int(n_host[0])
+        if n > cap:
+            _CAPACITY[key] = int(n * 1.25) + 65536
+            return n
+        if n * 2 < cap:  # shrink slowly when the scene got much lighter
+            _CAPACITY[key] = max(int(n * 1.25) + 65536, int(cap * 0.9))
+        return None
+
+    return idx_sorted, tile_range, check
+
+
 def sort_gaussian(uv: Tensor, depth: Tensor, W: int, H: int, radius: Tensor, tiles: Tensor, return_keys: bool = False):
     """Sort Gaussians by [tile|depth] -> (idx_sorted[N] int32, tile_range[tiles,2] int32)."""
     uv_c, d_c = _f32(uv.detach(), "uv"), _f32(depth.detach(), "depth").reshape(-1)
