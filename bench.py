@@ -310,11 +310,13 @@ def main():
     N_mean = sum(Ns) / len(Ns)
     Cch, S = 3, 12
     tiles = ((W + 15) // 16) * ((H + 15) // 16)
-    passes = (32 + (tiles - 1).bit_length() + 7) // 8
+    passes = max(1, ((tiles - 1).bit_length() + 7) // 8)
     alg = {
         "pxb_fused_forward": P * (12 + 12 + 16 + 4 + 192 + 4 * S + 4 + 4 + 4),
-        "pxb_tile_scan": P * 8,
-        "pxb_sort_gaussian": P * 28 + N_mean * 12 + N_mean * (8 + 24 * passes) + N_mean * 8 + tiles * 8,
+        # depth-order sort of P (key,id) pairs: init 12 + histogram 4 + 4 passes x 16 B, gathered scan 16 B
+        "pxb_bin_prepare": P * (12 + 4 + 4 * 16 + 16),
+        # emit (28 B/Gaussian read, 8 B/isect written), histogram 4, tile passes x 16 B, ranges 4 B/isect + 8 B/tile
+        "pxb_sort_gaussian": P * 28 + N_mean * (8 + 4 + 16 * passes + 4) + tiles * 8,
         "pxb_blend_forward": N_mean * (4 + 4 * S) + 4 * (Cch + 2) * H * W,
         "pxb_blend_backward": N_mean * (4 + 4 * S) + (4 * Cch + 8) * H * W + N_mean * 8 * (6 + Cch),
         "pxb_fused_backward": P * (4 * S + 12 + 12 + 16 + 192 + 4 + 4 + 12 + 12 + 16 + 4 + 192 + 8),

@@ -73,25 +73,25 @@ int pxb_compute_sh_forward(int P, int C, int D, const float* shs, const float* d
 int pxb_compute_sh_backward(int P, int C, int D, const float* shs, const float* dirs, const uint8_t* visible,
                             const float* dL_dval, float* dL_dshs, float* dL_ddirs, void* stream);
 
-/* ---- tile binning: replaces torch.cumsum + computeGaussianKey + torch.sort +
- *      torch.gather + computeTileGaussianRange
- *      (msplat/msplat/sort_gaussian.py:42-52, include/sort_gaussian.h, src/sort_gaussian.cu:74-142) ---- */
-size_t pxb_binning_workspace_bytes(int P, long long N_cap, int W, int H);
-/* offsets_incl[P] = inclusive cumsum(tiles); *total_dev = offsets_incl[P-1] (device int). */
-int pxb_tile_scan(int P, const int* tiles, int* offsets_incl, int* total_dev, void* ws, size_t ws_bytes, void* stream);
-/* N = number of intersections (host value of *total_dev).  uv may be strided
- * (uv_stride floats between Gaussians) so the packed record can be passed.
- * idx_sorted[N] i32, tile_range[tiles,2] i32; keys_sorted_out[N] i64 optional (NULL to skip). */
-int pxb_sort_gaussian(int P, long long N, const float* uv, int uv_stride, const float* depth, const int* radius,
-                      const int* tiles, const int* offsets_incl, int W, int H, int* idx_sorted, int* tile_range,
-                      long long* keys_sorted_out, void* ws, size_t ws_bytes, void* stream);
-
-/* Sync-free variant used by the fused plugin path: grids/buffers sized for N_cap, the kernels read the
- * actual intersection count from *total_dev and process min(*total_dev, N_cap) entries; the caller
- * verifies *total_dev <= N_cap afterwards (asynchronously) and re-runs with more capacity otherwise. */
-int pxb_sort_gaussian_dev(int P, long long N_cap, const int* total_dev, const float* uv, int uv_stride,
-                          const float* depth, const int* radius, const int* tiles, const int* offsets_incl, int W,
-                          int H, int* idx_sorted, int* tile_range, void* ws, size_t ws_bytes, void* stream);
+/* ---- tile binning: replaces torch.cumsum + computeGaussianKey + torch.sort + torch.gather +
+ *      computeTileGaussianRange (msplat/msplat/sort_gaussian.py:42-52, include/sort_gaussian.h,
+ *      src/sort_gaussian.cu:74-142).  Two calls sharing a P-sized workspace:
+ *      pxb_bin_prepare depth-orders the Gaussians and counts the intersections (*total_dev, device int);
+ *      pxb_sort_gaussian emits (tile, id) pairs in that order, radix-sorts them by tile and extracts
+ *      the ranges.  Output order == the reference's stable sort of tile<<32|depth keys. ---- */
+size_t pxb_bin_prepare_workspace_bytes(int P);
+size_t pxb_bin_sort_workspace_bytes(long long N_cap, int W, int H);
+int pxb_bin_prepare(int P, const float* depth, const int* radius, const int* tiles, int* total_dev, void* ws_p,
+                    size_t ws_p_bytes, void* stream);
+/* N: the exact intersection count when total_dev == NULL (the caller read *total_dev back), otherwise a
+ * capacity: grids/buffers are sized for N, the kernels process min(*total_dev, N) entries and the caller
+ * verifies *total_dev <= N afterwards (re-running with more capacity if not) -- no host round trip.
+ * uv may be strided (uv_stride floats between Gaussians) so the packed record can be passed.
+ * idx_sorted[N] i32, tile_range[tiles,2] i32; keys_sorted_out[N] i64 optional (NULL to skip; exact-N mode only). */
+int pxb_sort_gaussian(int P, long long N, const int* total_dev, const float* uv, int uv_stride, const float* depth,
+                      const int* radius, const int* tiles, int W, int H, int* idx_sorted, int* tile_range,
+                      long long* keys_sorted_out, void* ws_p, size_t ws_p_bytes, void* ws_n, size_t ws_n_bytes,
+                      void* stream);
 
 /* ---- alpha blending: replaces alphaBlendingForward/Backward
  *      (include/alpha_blending.h, src/alpha_blending.cu:248-572) ---- */

@@ -29,10 +29,10 @@ SIGNATURES = {
     "pxb_ewa_project_backward": (i32, [i32, p, p, p, p, p, p, p, p, p, p, p]),
     "pxb_compute_sh_forward": (i32, [i32, i32, i32, p, p, p, p, p]),
     "pxb_compute_sh_backward": (i32, [i32, i32, i32, p, p, p, p, p, p, p]),
-    "pxb_binning_workspace_bytes": (sz, [i32, i64, i32, i32]),
-    "pxb_tile_scan": (i32, [i32, p, p, p, p, sz, p]),
-    "pxb_sort_gaussian": (i32, [i32, i64, p, i32, p, p, p, p, i32, i32, p, p, p, p, sz, p]),
-    "pxb_sort_gaussian_dev": (i32, [i32, i64, p, p, i32, p, p, p, p, i32, i32, p, p, p, sz, p]),
+    "pxb_bin_prepare_workspace_bytes": (sz, [i32]),
+    "pxb_bin_sort_workspace_bytes": (sz, [i64, i32, i32]),
+    "pxb_bin_prepare": (i32, [i32, p, p, p, p, p, sz, p]),
+    "pxb_sort_gaussian": (i32, [i32, i64, p, p, i32, p, p, p, i32, i32, p, p, p, p, sz, p, sz, p]),
     "pxb_record_stride": (i32, [i32]),
     "pxb_pack_records": (i32, [i32, p, p, p, p, i32, i32, i32, i32, p, p]),
     "pxb_unpack_grads": (i32, [i32, p, i32, i32, i32, i32, i32, p, p, p, p, p]),
@@ -79,7 +79,7 @@ def ensure_init() -> None:
 KERNELS_PER_CALL = {
     "pxb_project_point_forward": 1, "pxb_project_point_backward": 1, "pxb_compute_cov3d_forward": 1,
     "pxb_compute_cov3d_backward": 1, "pxb_ewa_project_forward": 1, "pxb_ewa_project_backward": 1,
-    "pxb_compute_sh_forward": 1, "pxb_compute_sh_backward": 1, "pxb_tile_scan": 1, "pxb_sort_gaussian": 4, "pxb_sort_gaussian_dev": 4,
+    "pxb_compute_sh_forward": 1, "pxb_compute_sh_backward": 1, "pxb_bin_prepare": 8, "pxb_sort_gaussian": 4,
     "pxb_pack_records": 1, "pxb_unpack_grads": 1, "pxb_blend_forward": 1, "pxb_blend_backward": 1,
     "pxb_fused_forward": 1, "pxb_fused_backward": 1,
 }
@@ -116,13 +116,10 @@ def launch(name: str, *args) -> None:
     global launch_count
     fn = getattr(lib, name)
     n = KERNELS_PER_CALL.get(name, 1)
-    if name == "pxb_sort_gaussian_dev":
-        W, H = args[9], args[10]
-        n += (32 + max(((W + 15) // 16) * ((H + 15) // 16) - 1, 0).bit_length() + 7) // 8
     if name == "pxb_sort_gaussian":
         W, H = args[8], args[9]
         nt = ((W + 15) // 16) * ((H + 15) // 16)
-        n += (32 + max(nt - 1, 0).bit_length() + 7) // 8 if args[1] > 0 else -4
+        n = (4 + max(1, (max(nt - 1, 0).bit_length() + 7) // 8)) if args[1] > 0 else 0
     launch_count += n
     if _timer is None:
         check(fn(*args), name)

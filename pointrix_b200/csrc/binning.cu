@@ -1,22 +1,26 @@
 // Tile binning (reference: msplat/msplat/sort_gaussian.py:42-52 and
-// msplat/msplat/src/sort_gaussian.cu:17-71):
-//   1. inclusive prefix sum of tiles-touched        (torch.cumsum in the reference)
-//   2. key emission: key = tile<<32 | depth bits, value = Gaussian id, emitted
-//      in ascending Gaussian id / row-major tile order, warp-cooperatively so
-//      every store is coalesced and big Gaussians do not serialise one thread
-//   3. stable LSD radix sort of (key,value) pairs, onesweep style (one global
-//      histogram pass, then one read + one write of the pairs per 8-bit digit
-//      with decoupled look-back), restricted to the 32 + ceil(log2 tiles) key
-//      bits that can be non-zero                    (torch.sort + gather in the reference)
-//   4. per-tile [first,last) ranges from the sorted keys.
-// Integer work throughout: results are bit-identical to the reference's.
+// msplat/msplat/src/sort_gaussian.cu:17-71).
+//
+// The reference sorts all N tile intersections by the 64-bit key tile<<32|depth (torch.sort, 8 radix
+// passes over N pairs + a gather).  The same order -- ascending (tile, depth bits), ties in
+// emission order = ascending Gaussian id -- is produced here with far less traffic:
+//   1. stable LSD radix sort of the P Gaussians by depth bits (4 passes over P, P << N);
+//   2. inclusive prefix sum of tiles-touched in that order (single pass, decoupled look-back);
+//   3. key emission in depth order: (tile id, Gaussian id) pairs, warp-cooperative so every store
+//      is coalesced and big Gaussians do not serialise one thread;
+//   4. stable radix sort of the N pairs by TILE ID ONLY (ceil(log2 tiles)/8 = 2 passes at 1080p):
+//      stability carries the (depth, id) order of step 1 into every tile;
+//   5. per-tile [first,last) ranges from the sorted tile ids.
+// All radix passes are onesweep style (one histogram pass, then one read + one write of the pairs
+// per 8-bit digit with decoupled look-back).  Integer work throughout: idx_sorted and tile_range
+// are bit-identical to the reference's; the 64-bit sorted keys can be rebuilt for inspection.
 #include "common.cuh"
 #include "pointrix_b200.h"
 
 namespace pxb {
 
 // ---------------------------------------------------------------------------
-// 1. single-pass inclusive scan (decoupled look-back), int32
+// single-pass inclusive scan (decoupled look-back, warp-parallel), int32, with an optional gather
 // ---------------------------------------------------------------------------
 constexpr int kScanThreads = 256;
 constexpr int kScanItems = 8;
@@ -24,9 +28,10 @@ constexpr int kScanTile = kScanThreads * kScanItems;
 #define kFlagAgg (1ull << 32)
 #define kFlagPrefix (2ull << 32)
 
+// out[i] = sum_{j<=i} cnt(order[j]),  cnt(g) = radius[g] > 0 ? tiles[g] : 0
 __global__ void __launch_bounds__(kScanThreads)
-scan_kernel(int P, const int* __restrict__ in, int* __restrict__ out, int* __restrict__ total,
-            unsigned long long* status, unsigned int* ticket) {
+scan_kernel(int P, const int* __restrict__ tiles, const int* __restrict__ radius, const unsigned int* __restrict__ order,
+            int* __restrict__ out, int* __restrict__ total, unsigned long long* status, unsigned int* ticket) {
     __shared__ int s_warp[kScanThreads / 32];
     __shared__ int s_tile, s_excl;
     if (threadIdx.x == 0) s_tile = (int)atomicAdd(ticket, 1u);
@@ -37,10 +42,13 @@ scan_kernel(int P, const int* __restrict__ in, int* __restrict__ out, int* __res
     int sum = 0;
 #pragma unroll
     for (int k = 0; k < kScanItems; k++) {
-        v[k] = (base + k < P) ? in[base + k] : 0;
+        v[k] = 0;
+        if (base + k < P) {
+            const int g = order ? (int)order[base + k] : base + k;
+            v[k] = (radius == nullptr || radius[g] > 0) ? tiles[g] : 0;
+        }
         sum += v[k];
     }
-    // block exclusive scan of per-thread sums
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     int incl = sum;
 #pragma unroll
@@ -69,9 +77,9 @@ scan_kernel(int P, const int* __restrict__ in, int* __restrict__ out, int* __res
             const unsigned int flag = (unsigned int)(sv >> 32);
             const unsigned int zero = __ballot_sync(0xffffffffu, flag == 0);
             const unsigned int pref = __ballot_sync(0xffffffffu, flag == 2);
-            const int first = pref ? (__ffs(pref) - 1) : 32;          // nearest tile holding an inclusive prefix
+            const int first = pref ? (__ffs(pref) - 1) : 32;  // nearest tile holding an inclusive prefix
             const unsigned int need = (first < 32) ? ((2u << first) - 1u) : 0xffffffffu;
-            if (zero & need) continue;                                 // some needed predecessor not published yet
+            if (zero & need) continue;  // some needed predecessor not published yet
             int v_ = (lane <= first) ? (int)(unsigned int)sv : 0;
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) v_ += __shfl_xor_sync(0xffffffffu, v_, o);
@@ -94,34 +102,43 @@ scan_kernel(int P, const int* __restrict__ in, int* __restrict__ out, int* __res
     }
 }
 
+// depth bits + identity permutation: the input of the Gaussian-order sort
+__global__ void init_depth_keys_kernel(int P, const float* __restrict__ depth, unsigned int* __restrict__ keys,
+                                       unsigned int* __restrict__ vals) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P) return;
+    keys[i] = __float_as_uint(depth[i]);
+    vals[i] = (unsigned int)i;
+}
+
 // ---------------------------------------------------------------------------
-// 2. key emission
+// key emission: sorted position i holds Gaussian g = order[i]; its tile ids go to
+// [offs_incl[i] - cnt, offs_incl[i])
 // ---------------------------------------------------------------------------
 constexpr int kEmitThreads = 256;
 
 __global__ void __launch_bounds__(kEmitThreads)
-emit_keys_kernel(int P, const float* __restrict__ uv, int uv_stride, const float* __restrict__ depth,
-                 const int* __restrict__ radius, const int* __restrict__ tiles, const int* __restrict__ offs_incl,
-                 int gx, int gy, long long N_cap, const int* __restrict__ n_dev,
-                 unsigned long long* __restrict__ keys, unsigned int* __restrict__ vals) {
+emit_keys_kernel(int P, const float* __restrict__ uv, int uv_stride, const int* __restrict__ radius,
+                 const int* __restrict__ tiles, const unsigned int* __restrict__ order,
+                 const int* __restrict__ offs_incl, int gx, int gy, long long N_cap, const int* __restrict__ n_dev,
+                 unsigned int* __restrict__ keys, unsigned int* __restrict__ vals) {
     const long long N = n_dev ? min((long long)*n_dev, N_cap) : N_cap;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
-    int x0 = 0, y0 = 0, w = 0, cnt = 0, off = 0;
-    unsigned int dbits = 0;
+    int x0 = 0, y0 = 0, w = 1, cnt = 0, off = 0, g = 0;
     if (i < P) {
-        const int r = radius[i];
+        g = (int)order[i];
+        const int r = radius[g];
         if (r > 0) {
             int x1, y1;
-            tile_rect(uv[(size_t)i * uv_stride], uv[(size_t)i * uv_stride + 1], r, gx, gy, x0, y0, x1, y1);
-            w = x1 - x0;
-            cnt = w * (y1 - y0);
-            off = offs_incl[i] - tiles[i];  // cumsum(tiles)[i-1]  (sort_gaussian.cu:33)
-            dbits = __float_as_uint(depth[i]);
+            tile_rect(uv[(size_t)g * uv_stride], uv[(size_t)g * uv_stride + 1], r, gx, gy, x0, y0, x1, y1);
+            w = max(x1 - x0, 1);
+            cnt = tiles[g];  // == w * (y1 - y0) (ewa_project.cu:81); the scan used the same count
+            off = offs_incl[i] - cnt;
         }
     }
-    // warp-cooperative expansion: slot s of the warp's cnt-sum belongs to the lane
-    // whose inclusive prefix first exceeds s
+    // warp-cooperative expansion: slot s of the warp's cnt-sum belongs to the lane whose inclusive
+    // prefix first exceeds s
     int incl = cnt;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -131,56 +148,52 @@ emit_keys_kernel(int P, const float* __restrict__ uv, int uv_stride, const float
     const int total = __shfl_sync(0xffffffffu, incl, 31);
     const int excl = incl - cnt;
     for (int s = lane; s < ((total + 31) & ~31); s += 32) {
-        // binary search over the 32 inclusive prefixes (held one per lane)
-        int lo = 0;
+        int lo = 0;  // binary search over the 32 inclusive prefixes (held one per lane)
 #pragma unroll
         for (int step = 16; step > 0; step >>= 1) {
             const int probe = __shfl_sync(0xffffffffu, incl, lo + step - 1);
             if (probe <= s) lo += step;
         }
-        // lo = first lane with incl > s   (s < total guarantees lo <= 31)
         const int src = min(lo, 31);
         const int e_src = __shfl_sync(0xffffffffu, excl, src);
         const int x0s = __shfl_sync(0xffffffffu, x0, src);
         const int y0s = __shfl_sync(0xffffffffu, y0, src);
         const int ws = __shfl_sync(0xffffffffu, w, src);
         const int offs = __shfl_sync(0xffffffffu, off, src);
-        const unsigned int db = __shfl_sync(0xffffffffu, dbits, src);
+        const int gs = __shfl_sync(0xffffffffu, g, src);
         if (s < total) {
             const int local = s - e_src;
             const int row = local / ws, col = local - row * ws;
-            const long long tile_id = (long long)(y0s + row) * gx + (x0s + col);
-            const long long key = (tile_id << 32) | (long long)(int)db;  // sign-extending OR as the reference
             const long long pos = (long long)offs + local;
             if (pos >= 0 && pos < N) {
-                keys[pos] = (unsigned long long)key;
-                vals[pos] = (unsigned int)(blockIdx.x * blockDim.x + (threadIdx.x & ~31) + src);
+                keys[pos] = (unsigned int)((y0s + row) * gx + (x0s + col));
+                vals[pos] = (unsigned int)gs;
             }
         }
     }
 }
 
 // ---------------------------------------------------------------------------
-// 3. onesweep LSD radix sort, 8-bit digits, 64-bit keys + 32-bit values
+// onesweep LSD radix sort, 8-bit digits, 32-bit keys + 32-bit values
 // ---------------------------------------------------------------------------
 constexpr int kRsThreads = 256;
 constexpr int kRsItems = 16;
-constexpr int kRsTile = kRsThreads * kRsItems;  // 4096 pairs per block
+constexpr int kRsTile = kRsThreads * kRsItems;  // 4096 pairs per CTA
 constexpr int kRadix = 256;
-constexpr int kMaxPasses = 8;
+constexpr int kMaxPasses = 4;
 #define kStAgg (1u << 30)
 #define kStPrefix (2u << 30)
 #define kStMask ((1u << 30) - 1u)
 
 __global__ void __launch_bounds__(kRsThreads)
-rs_histogram_kernel(const unsigned long long* __restrict__ keys, int N_cap, const int* __restrict__ n_dev, int passes,
+rs_histogram_kernel(const unsigned int* __restrict__ keys, int N_cap, const int* __restrict__ n_dev, int passes,
                     unsigned int* __restrict__ hist) {
     __shared__ unsigned int h[kMaxPasses][kRadix];
     const int N = n_dev ? min(*n_dev, N_cap) : N_cap;
     for (int k = threadIdx.x; k < kMaxPasses * kRadix; k += blockDim.x) (&h[0][0])[k] = 0;
     __syncthreads();
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (long long)gridDim.x * blockDim.x) {
-        const unsigned long long k = keys[i];
+        const unsigned int k = keys[i];
         for (int p = 0; p < passes; p++) atomicAdd(&h[p][(k >> (8 * p)) & 255u], 1u);
     }
     __syncthreads();
@@ -210,7 +223,7 @@ __global__ void rs_scan_hist_kernel(unsigned int* __restrict__ hist) {
 }
 
 struct RsSmem {
-    unsigned long long keys[kRsTile];
+    unsigned int keys[kRsTile];
     unsigned int vals[kRsTile];
     unsigned int warp_hist[kRsThreads / 32][kRadix];
     unsigned int digit_start[kRadix];
@@ -220,13 +233,12 @@ struct RsSmem {
 };
 
 __global__ void __launch_bounds__(kRsThreads)
-rs_onesweep_kernel(const unsigned long long* __restrict__ keys_in, const unsigned int* __restrict__ vals_in,
-                   unsigned long long* __restrict__ keys_out, unsigned int* __restrict__ vals_out, int N_cap,
+rs_onesweep_kernel(const unsigned int* __restrict__ keys_in, const unsigned int* __restrict__ vals_in,
+                   unsigned int* __restrict__ keys_out, unsigned int* __restrict__ vals_out, int N_cap,
                    const int* __restrict__ n_dev, int shift, const unsigned int* __restrict__ bin_base /*[256] exclusive*/,
                    unsigned int* status, unsigned int* ticket) {
     const int N = n_dev ? min(*n_dev, N_cap) : N_cap;
-    extern __shared__ __align__(16) unsigned char rs_raw[];
-    RsSmem& sm = *reinterpret_cast<RsSmem*>(rs_raw);
+    __shared__ RsSmem sm;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) sm.tile = (int)atomicAdd(ticket, 1u);
     for (int k = tid; k < (kRsThreads / 32) * kRadix; k += kRsThreads) (&sm.warp_hist[0][0])[k] = 0;
@@ -237,7 +249,7 @@ rs_onesweep_kernel(const unsigned long long* __restrict__ keys_in, const unsigne
     const int tile_n = (int)min((long long)kRsTile, (long long)N - tile_base);
 
     // warp-striped load: item k of lane l in warp w sits at w*32*IPT + k*32 + l
-    unsigned long long key[kRsItems];
+    unsigned int key[kRsItems];
     unsigned int val[kRsItems];
     unsigned int rank[kRsItems];
     const int wbase = warp * 32 * kRsItems + lane;
@@ -248,35 +260,27 @@ rs_onesweep_kernel(const unsigned long long* __restrict__ keys_in, const unsigne
             key[k] = keys_in[tile_base + p];
             val[k] = vals_in[tile_base + p];
         } else {
-            key[k] = ~0ull;
+            key[k] = ~0u;
             val[k] = 0;
         }
     }
     // warp-level stable ranking; counters private to the warp.  The peer masks of all items are
-    // computed first (independent work that pipelines); only the short leader read-modify-write
-    // of the warp-private counter is serial per item.
+    // computed first (independent, they pipeline); only the short leader read-modify-write of the
+    // warp-private counter is serial per item.
     const unsigned int lt_mask = (1u << lane) - 1u;
     unsigned int* wh = sm.warp_hist[warp];
     unsigned int peers[kRsItems];
 #pragma unroll
     for (int k = 0; k < kRsItems; k++) {
         const bool valid = (wbase + k * 32) < tile_n;
-        const unsigned int d = (unsigned int)(key[k] >> shift) & 255u;
+        const unsigned int d = (key[k] >> shift) & 255u;
         const unsigned int vmask = __ballot_sync(0xffffffffu, valid);
-        // lanes holding the same digit: eight ballots (MATCH.ANY proved to be the pass's bottleneck:
-        // ~40 % of the stall samples sat on its consumer in the first profile)
-        unsigned int m = vmask;
-#pragma unroll
-        for (int b = 0; b < 8; b++) {
-            const bool bit = (d >> b) & 1u;
-            const unsigned int bal = __ballot_sync(0xffffffffu, bit);
-            m &= bit ? bal : ~bal;
-        }
-        peers[k] = valid ? m : 0u;
+        const unsigned int m = __match_any_sync(0xffffffffu, d);  // all lanes participate
+        peers[k] = valid ? (m & vmask) : 0u;
     }
 #pragma unroll
     for (int k = 0; k < kRsItems; k++) {
-        const unsigned int d = (unsigned int)(key[k] >> shift) & 255u;
+        const unsigned int d = (key[k] >> shift) & 255u;
         unsigned int old = 0;
         const int leader = peers[k] ? (__ffs(peers[k]) - 1) : 0;
         if (peers[k] && lane == leader) {
@@ -346,7 +350,7 @@ rs_onesweep_kernel(const unsigned long long* __restrict__ keys_in, const unsigne
 #pragma unroll
     for (int k = 0; k < kRsItems; k++) {
         if ((wbase + k * 32) < tile_n) {
-            const unsigned int d = (unsigned int)(key[k] >> shift) & 255u;
+            const unsigned int d = (key[k] >> shift) & 255u;
             const unsigned int pos = sm.digit_start[d] + sm.warp_hist[warp][d] + rank[k];
             sm.keys[pos] = key[k];
             sm.vals[pos] = val[k];
@@ -358,8 +362,8 @@ rs_onesweep_kernel(const unsigned long long* __restrict__ keys_in, const unsigne
     for (int k = 0; k < kRsItems; k++) {
         const int p = k * kRsThreads + tid;
         if (p < tile_n) {
-            const unsigned long long kk = sm.keys[p];
-            const unsigned int d = (unsigned int)(kk >> shift) & 255u;
+            const unsigned int kk = sm.keys[p];
+            const unsigned int d = (kk >> shift) & 255u;
             const long long dst = sm.gbase[d] + p;
             keys_out[dst] = kk;
             vals_out[dst] = sm.vals[p];
@@ -368,25 +372,32 @@ rs_onesweep_kernel(const unsigned long long* __restrict__ keys_in, const unsigne
 }
 
 // ---------------------------------------------------------------------------
-// 4. tile ranges (sort_gaussian.cu:45-71)
+// tile ranges (sort_gaussian.cu:45-71) from the sorted tile ids
 // ---------------------------------------------------------------------------
-__global__ void tile_range_kernel(int N_cap, const int* __restrict__ n_dev,
-                                  const unsigned long long* __restrict__ keys_sorted, int num_tiles,
-                                  int2* __restrict__ tile_range) {
+__global__ void tile_range_kernel(int N_cap, const int* __restrict__ n_dev, const unsigned int* __restrict__ tile_sorted,
+                                  int num_tiles, int2* __restrict__ tile_range) {
     const int N = n_dev ? min(*n_dev, N_cap) : N_cap;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N) return;
-    const int cur = (int)(keys_sorted[i] >> 32);
-    if ((unsigned)cur >= (unsigned)num_tiles) return;  // negative-depth keys: undefined in the reference
+    const unsigned int cur = tile_sorted[i];
+    if (cur >= (unsigned)num_tiles) return;
     if (i == 0) tile_range[cur].x = 0;
     else {
-        const int prev = (int)(keys_sorted[i - 1] >> 32);
+        const unsigned int prev = tile_sorted[i - 1];
         if (prev != cur) {
             tile_range[cur].x = i;
-            if ((unsigned)prev < (unsigned)num_tiles) tile_range[prev].y = i;
+            if (prev < (unsigned)num_tiles) tile_range[prev].y = i;
         }
     }
     if (i == N - 1) tile_range[cur].y = N;
+}
+
+// the reference's sorted int64 keys, rebuilt for inspection / tests
+__global__ void rebuild_keys_kernel(int N, const unsigned int* __restrict__ tile_sorted, const int* __restrict__ idx_sorted,
+                                    const float* __restrict__ depth, long long* __restrict__ keys) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    keys[i] = ((long long)tile_sorted[i] << 32) | (long long)(int)__float_as_uint(depth[idx_sorted[i]]);
 }
 
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -395,41 +406,75 @@ static inline int ceil_log2(int x) {
     while ((1ll << b) < x) b++;
     return b;
 }
-static inline int sort_passes(int num_tiles) { return (32 + ceil_log2(num_tiles) + 7) / 8; }
+static inline int tile_passes(int num_tiles) { return max(1, (ceil_log2(num_tiles) + 7) / 8); }
 
-struct BinWs {
-    unsigned char* ctl;      // zeroed region: scan status/ticket, histograms, onesweep status/tickets
-    size_t ctl_bytes;
-    unsigned long long* scan_status;
-    unsigned int* scan_ticket;
-    unsigned int* hist;
-    unsigned int* rs_ticket;
-    unsigned int* rs_status;
-    unsigned long long* keys0;
-    unsigned long long* keys1;
-    unsigned int* vals_tmp;
+// P-sized workspace: survives from pxb_bin_prepare to pxb_sort_gaussian
+struct WsP {
+    unsigned char* ctl; size_t ctl_bytes;          // zeroed per call
+    unsigned long long* scan_status; unsigned int* scan_ticket;
+    unsigned int* hist; unsigned int* rs_ticket; unsigned int* rs_status;
+    unsigned int* keys[2]; unsigned int* vals[2];  // depth-sort ping-pong; result in keys[0]/vals[0] (4 passes)
+    int* offsets;
     size_t total;
 };
-
-static BinWs carve(void* ws, int P, long long Ncap, int num_tiles) {
-    BinWs b;
-    const int passes = sort_passes(num_tiles);
+static WsP carve_p(void* ws, int P) {
+    WsP b;
     const size_t scan_tiles = (size_t)(P + kScanTile - 1) / kScanTile + 1;
-    const size_t rs_tiles = (size_t)((Ncap + kRsTile - 1) / kRsTile) + 1;
+    const size_t rs_tiles = (size_t)(P + kRsTile - 1) / kRsTile + 1;
     size_t o = 0;
     unsigned char* base = (unsigned char*)ws;
     b.ctl = base;
     b.scan_status = (unsigned long long*)(base + o); o += align_up(scan_tiles * 8, 256);
     b.scan_ticket = (unsigned int*)(base + o); o += 256;
+    b.hist = (unsigned int*)(base + o); o += align_up((size_t)4 * kRadix * 4, 256);
+    b.rs_ticket = (unsigned int*)(base + o); o += 256;
+    b.rs_status = (unsigned int*)(base + o); o += align_up((size_t)4 * rs_tiles * kRadix * 4, 256);
+    b.ctl_bytes = o;
+    for (int k = 0; k < 2; k++) {
+        b.keys[k] = (unsigned int*)(base + o); o += align_up((size_t)P * 4, 256);
+        b.vals[k] = (unsigned int*)(base + o); o += align_up((size_t)P * 4, 256);
+    }
+    b.offsets = (int*)(base + o); o += align_up((size_t)P * 4, 256);
+    b.total = o;
+    return b;
+}
+// N-sized workspace of pxb_sort_gaussian
+struct WsN {
+    unsigned char* ctl; size_t ctl_bytes;
+    unsigned int* hist; unsigned int* rs_ticket; unsigned int* rs_status;
+    unsigned int* keys[2]; unsigned int* vals_tmp;
+    size_t total;
+};
+static WsN carve_n(void* ws, long long Ncap, int num_tiles) {
+    WsN b;
+    const int passes = tile_passes(num_tiles);
+    const size_t rs_tiles = (size_t)((Ncap + kRsTile - 1) / kRsTile) + 1;
+    size_t o = 0;
+    unsigned char* base = (unsigned char*)ws;
+    b.ctl = base;
     b.hist = (unsigned int*)(base + o); o += align_up((size_t)kMaxPasses * kRadix * 4, 256);
     b.rs_ticket = (unsigned int*)(base + o); o += 256;
     b.rs_status = (unsigned int*)(base + o); o += align_up((size_t)passes * rs_tiles * kRadix * 4, 256);
     b.ctl_bytes = o;
-    b.keys0 = (unsigned long long*)(base + o); o += align_up((size_t)Ncap * 8, 256);
-    b.keys1 = (unsigned long long*)(base + o); o += align_up((size_t)Ncap * 8, 256);
+    for (int k = 0; k < 2; k++) { b.keys[k] = (unsigned int*)(base + o); o += align_up((size_t)Ncap * 4, 256); }
     b.vals_tmp = (unsigned int*)(base + o); o += align_up((size_t)Ncap * 4, 256);
     b.total = o;
     return b;
+}
+
+// one stable LSD radix sort over `passes` 8-bit digits starting at bit 0; result lands in (k[passes&1], v[passes&1])
+static int radix_sort_u32(unsigned int* k[2], unsigned int* v[2], int N_cap, const int* n_dev, int passes,
+                          unsigned int* hist, unsigned int* status, unsigned int* ticket, cudaStream_t s) {
+    const int rs_tiles = (N_cap + kRsTile - 1) / kRsTile;
+    const int hist_blocks = (int)min((long long)(148 * 8), ((long long)N_cap + kRsThreads * 8 - 1) / (kRsThreads * 8));
+    rs_histogram_kernel<<<hist_blocks, kRsThreads, 0, s>>>(k[0], N_cap, n_dev, passes, hist);
+    rs_scan_hist_kernel<<<passes, kRadix, 0, s>>>(hist);
+    for (int p = 0; p < passes; p++) {
+        rs_onesweep_kernel<<<rs_tiles, kRsThreads, 0, s>>>(k[p & 1], v[p & 1], k[(p + 1) & 1], v[(p + 1) & 1], N_cap, n_dev,
+                                                          8 * p, hist + p * kRadix,
+                                                          status + (size_t)p * (rs_tiles + 1) * kRadix, ticket + p);
+    }
+    return (int)cudaGetLastError();
 }
 
 }  // namespace pxb
@@ -438,85 +483,61 @@ using namespace pxb;
 
 extern "C" {
 
-size_t pxb_binning_workspace_bytes(int P, long long N_cap, int W, int H) {
+size_t pxb_bin_prepare_workspace_bytes(int P) { return carve_p(nullptr, P > 0 ? P : 1).total; }
+
+size_t pxb_bin_sort_workspace_bytes(long long N_cap, int W, int H) {
     const int gx = (W + PXB_TILE - 1) / PXB_TILE, gy = (H + PXB_TILE - 1) / PXB_TILE;
-    if (N_cap < 1) N_cap = 1;
-    return carve(nullptr, P > 0 ? P : 1, N_cap, gx * gy).total;
+    return carve_n(nullptr, N_cap > 0 ? N_cap : 1, gx * gy).total;
 }
 
-// inclusive cumsum of tiles (int32) + total on the device
-int pxb_tile_scan(int P, const int* tiles, int* offsets_incl, int* total_dev, void* ws, size_t ws_bytes,
-                  void* stream) {
+// Depth-order the Gaussians and prefix-sum their tile counts in that order.
+// *total_dev = number of intersections N.  ws_p must stay untouched until pxb_sort_gaussian.
+int pxb_bin_prepare(int P, const float* depth, const int* radius, const int* tiles, int* total_dev, void* ws_p,
+                    size_t ws_p_bytes, void* stream) {
     cudaStream_t s = (cudaStream_t)stream;
     if (P <= 0) return (int)cudaMemsetAsync(total_dev, 0, sizeof(int), s);
-    const size_t scan_tiles = (size_t)(P + kScanTile - 1) / kScanTile + 1;
-    const size_t need = align_up(scan_tiles * 8, 256) + 256;
-    if (ws_bytes < need) return PXB_ERR_WORKSPACE;
-    unsigned long long* status = (unsigned long long*)ws;
-    unsigned int* ticket = (unsigned int*)((unsigned char*)ws + align_up(scan_tiles * 8, 256));
-    PXB_CUDA_OK(cudaMemsetAsync(ws, 0, need, s));
-    scan_kernel<<<(P + kScanTile - 1) / kScanTile, kScanThreads, 0, s>>>(P, tiles, offsets_incl, total_dev, status, ticket);
+    WsP b = carve_p(ws_p, P);
+    if (ws_p_bytes < b.total) return PXB_ERR_WORKSPACE;
+    PXB_CUDA_OK(cudaMemsetAsync(b.ctl, 0, b.ctl_bytes, s));
+    init_depth_keys_kernel<<<(P + 255) / 256, 256, 0, s>>>(P, depth, b.keys[0], b.vals[0]);
+    int rc = radix_sort_u32(b.keys, b.vals, P, nullptr, 4, b.hist, b.rs_status, b.rs_ticket, s);  // -> keys[0]/vals[0]
+    if (rc) return rc;
+    scan_kernel<<<(P + kScanTile - 1) / kScanTile, kScanThreads, 0, s>>>(P, tiles, radius, b.vals[0], b.offsets, total_dev,
+                                                                        b.scan_status, b.scan_ticket);
     return (int)cudaGetLastError();
 }
 
-static int sort_impl(int P, long long N, const int* n_dev, const float* uv, int uv_stride, const float* depth,
-                     const int* radius, const int* tiles, const int* offsets_incl, int W, int H, int* idx_sorted,
-                     int* tile_range, long long* keys_sorted_out, void* ws, size_t ws_bytes, cudaStream_t s) {
+// keys + tile sort + ranges.  N: exact count when total_dev == NULL, else a capacity: the kernels
+// then process min(*total_dev, N) intersections and the caller verifies *total_dev <= N afterwards.
+int pxb_sort_gaussian(int P, long long N, const int* total_dev, const float* uv, int uv_stride, const float* depth,
+                      const int* radius, const int* tiles, int W, int H, int* idx_sorted, int* tile_range,
+                      long long* keys_sorted_out /*nullable, [N]*/, void* ws_p, size_t ws_p_bytes, void* ws_n,
+                      size_t ws_n_bytes, void* stream) {
+    cudaStream_t s = (cudaStream_t)stream;
     const int gx = (W + PXB_TILE - 1) / PXB_TILE, gy = (H + PXB_TILE - 1) / PXB_TILE;
     const int num_tiles = gx * gy;
     PXB_CUDA_OK(cudaMemsetAsync(tile_range, 0, (size_t)num_tiles * 2 * sizeof(int), s));
     if (P <= 0 || N <= 0) return 0;
     if (N > 0x3fffffffll) return PXB_ERR_BAD_ARG;
-    BinWs b = carve(ws, P, N, num_tiles);
-    if (ws_bytes < b.total) return PXB_ERR_WORKSPACE;
-    const int passes = sort_passes(num_tiles);
-    const int rs_tiles = (int)((N + kRsTile - 1) / kRsTile);
-    PXB_CUDA_OK(cudaMemsetAsync(b.ctl, 0, b.ctl_bytes, s));
-    // choose the ping-pong start so that the last pass lands in idx_sorted
-    unsigned long long* kcur = b.keys0;
-    unsigned long long* kalt = b.keys1;
-    unsigned int* vcur = (passes % 2 == 0) ? (unsigned int*)idx_sorted : b.vals_tmp;
-    unsigned int* valt = (passes % 2 == 0) ? b.vals_tmp : (unsigned int*)idx_sorted;
+    WsP bp = carve_p(ws_p, P);
+    WsN bn = carve_n(ws_n, N, num_tiles);
+    if (ws_p_bytes < bp.total || ws_n_bytes < bn.total) return PXB_ERR_WORKSPACE;
+    const int passes = tile_passes(num_tiles);
+    PXB_CUDA_OK(cudaMemsetAsync(bn.ctl, 0, bn.ctl_bytes, s));
+    // ping-pong so that the last pass writes the values straight into idx_sorted
+    unsigned int* k[2] = {bn.keys[0], bn.keys[1]};
+    unsigned int* v[2];
+    v[passes & 1] = (unsigned int*)idx_sorted;
+    v[(passes + 1) & 1] = bn.vals_tmp;
     emit_keys_kernel<<<(P + kEmitThreads - 1) / kEmitThreads, kEmitThreads, 0, s>>>(
-        P, uv, uv_stride, depth, radius, tiles, offsets_incl, gx, gy, N, n_dev, kcur, vcur);
-    const int hist_blocks = (int)min((long long)(148 * 8), (N + kRsThreads * 8 - 1) / (kRsThreads * 8));
-    rs_histogram_kernel<<<hist_blocks, kRsThreads, 0, s>>>(kcur, (int)N, n_dev, passes, b.hist);
-    rs_scan_hist_kernel<<<passes, kRadix, 0, s>>>(b.hist);
-    static bool attr_set = false;
-    if (!attr_set) {
-        PXB_CUDA_OK(cudaFuncSetAttribute(rs_onesweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RsSmem)));
-        attr_set = true;
-    }
-    for (int p = 0; p < passes; p++) {
-        rs_onesweep_kernel<<<rs_tiles, kRsThreads, sizeof(RsSmem), s>>>(
-            kcur, vcur, kalt, valt, (int)N, n_dev, 8 * p, b.hist + p * kRadix,
-            b.rs_status + (size_t)p * (rs_tiles + 1) * kRadix, b.rs_ticket + p);
-        unsigned long long* tk = kcur; kcur = kalt; kalt = tk;
-        unsigned int* tv = vcur; vcur = valt; valt = tv;
-    }
-    tile_range_kernel<<<(int)((N + 255) / 256), 256, 0, s>>>((int)N, n_dev, kcur, num_tiles, (int2*)tile_range);
-    if (keys_sorted_out)
-        PXB_CUDA_OK(cudaMemcpyAsync(keys_sorted_out, kcur, (size_t)N * 8, cudaMemcpyDeviceToDevice, s));
+        P, uv, uv_stride, radius, tiles, bp.vals[0], bp.offsets, gx, gy, N, total_dev, k[0], v[0]);
+    int rc = radix_sort_u32(k, v, (int)N, total_dev, passes, bn.hist, bn.rs_status, bn.rs_ticket, s);
+    if (rc) return rc;
+    const unsigned int* tile_sorted = k[passes & 1];
+    tile_range_kernel<<<(int)((N + 255) / 256), 256, 0, s>>>((int)N, total_dev, tile_sorted, num_tiles, (int2*)tile_range);
+    if (keys_sorted_out && total_dev == nullptr)
+        rebuild_keys_kernel<<<(int)((N + 255) / 256), 256, 0, s>>>((int)N, tile_sorted, idx_sorted, depth, keys_sorted_out);
     return (int)cudaGetLastError();
-}
-
-// keys + sort + ranges.  N = offsets_incl[P-1] (the caller has read it back).
-int pxb_sort_gaussian(int P, long long N, const float* uv, int uv_stride, const float* depth, const int* radius,
-                      const int* tiles, const int* offsets_incl, int W, int H, int* idx_sorted, int* tile_range,
-                      long long* keys_sorted_out /*nullable, [N]*/, void* ws, size_t ws_bytes, void* stream) {
-    return sort_impl(P, N, nullptr, uv, uv_stride, depth, radius, tiles, offsets_incl, W, H, idx_sorted, tile_range,
-                     keys_sorted_out, ws, ws_bytes, (cudaStream_t)stream);
-}
-
-// Same, without a host round trip: buffers and grids are sized for N_cap, the kernels read the
-// actual count from *total_dev (written by pxb_tile_scan) and work on min(*total_dev, N_cap).
-// The caller checks *total_dev <= N_cap later (and re-runs with a larger capacity if not).
-int pxb_sort_gaussian_dev(int P, long long N_cap, const int* total_dev, const float* uv, int uv_stride,
-                          const float* depth, const int* radius, const int* tiles, const int* offsets_incl, int W,
-                          int H, int* idx_sorted, int* tile_range, void* ws, size_t ws_bytes, void* stream) {
-    if (total_dev == nullptr) return PXB_ERR_BAD_ARG;
-    return sort_impl(P, N_cap, total_dev, uv, uv_stride, depth, radius, tiles, offsets_incl, W, H, idx_sorted,
-                     tile_range, nullptr, ws, ws_bytes, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -192,6 +192,17 @@ def ewa_project(xyz: Tensor, cov3d: Tensor, intr: Tensor, extr: Tensor, uv: Tens
 # ---------------------------------------------------------------------------
 # sort_gaussian          msplat/msplat/sort_gaussian.py:8-54
 # ---------------------------------------------------------------------------
+def _prepare(depth: Tensor, radius: Tensor, tiles: Tensor, stream):
+    """depth-order the Gaussians + count intersections -> (total_dev[1], ws_p, ws_p_bytes)"""
+    dev = depth.device
+    P = radius.numel()
+    total = torch.empty(1, dtype=torch.int32, device=dev)
+    ws_p_bytes = lib.pxb_bin_prepare_workspace_bytes(P)
+    ws_p = torch.empty(ws_p_bytes, dtype=torch.uint8, device=dev)
+    launch("pxb_bin_prepare", P, _p(depth), _p(radius), _p(tiles), _p(total), _p(ws_p), ws_p_bytes, stream)
+    return total, ws_p, ws_p_bytes
+
+
 def _bin(uv_like: Tensor, uv_stride: int, depth: Tensor, radius: Tensor, tiles: Tensor, W: int, H: int,
          return_keys: bool = False):
     dev = depth.device
@@ -200,18 +211,14 @@ def _bin(uv_like: Tensor, uv_stride: int, depth: Tensor, radius: Tensor, tiles: 
     tile_range = torch.empty(n_tiles, 2, dtype=torch.int32, device=dev)
     with torch.cuda.device(dev):
         stream = _stream(dev)
-        offsets = torch.empty(max(P, 1), dtype=torch.int32, device=dev)
-        total = torch.empty(1, dtype=torch.int32, device=dev)
-        ws0_bytes = lib.pxb_binning_workspace_bytes(P, 1, int(W), int(H))
-        ws0 = torch.empty(ws0_bytes, dtype=torch.uint8, device=dev)
-        launch("pxb_tile_scan", P, _p(tiles), _p(offsets), _p(total), _p(ws0), ws0_bytes, stream)
-        N = int(total.item())  # the one host sync of the path (the reference has two)
+        total, ws_p, ws_p_bytes = _prepare(depth, radius, tiles, stream)
+        N = int(total.item())  # the one host sync of the operator path (the reference has two)
         idx_sorted = torch.empty(N, dtype=torch.int32, device=dev)
         keys = torch.empty(N, dtype=torch.int64, device=dev) if return_keys else None
-        ws_bytes = lib.pxb_binning_workspace_bytes(P, max(N, 1), int(W), int(H))
-        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-        launch("pxb_sort_gaussian", P, N, _p(uv_like), uv_stride, _p(depth), _p(radius), _p(tiles), _p(offsets), int(W),
-                                    int(H), _p(idx_sorted), _p(tile_range), _p(keys), _p(ws), ws_bytes, stream)
+        ws_n_bytes = lib.pxb_bin_sort_workspace_bytes(max(N, 1), int(W), int(H))
+        ws_n = torch.empty(ws_n_bytes, dtype=torch.uint8, device=dev)
+        launch("pxb_sort_gaussian", P, N, _p(None), _p(uv_like), uv_stride, _p(depth), _p(radius), _p(tiles), int(W), int(H),
+               _p(idx_sorted), _p(tile_range), _p(keys), _p(ws_p), ws_p_bytes, _p(ws_n), ws_n_bytes, stream)
     if return_keys:
         return idx_sorted, tile_range, keys
     return idx_sorted, tile_range
@@ -228,8 +235,8 @@ def _bin_nosync(uv_like: Tensor, uv_stride: int, depth: Tensor, radius: Tensor, 
     Buffers and grids are sized for a capacity learnt from earlier views; the kernels read the
     actual intersection count on the device.  Returns ``(idx_sorted[cap], tile_range, check)``
     where ``check()`` -- to be called once the rest of the forward has been queued -- waits for the
-    count (copied to pinned memory right after the scan), and returns None if it fitted or the
-    exact count if the capacity was exceeded (the caller then re-bins and re-blends; rare)."""
+    count (copied to pinned memory right after the prepare step), and returns None if it fitted or
+    the exact count if the capacity was exceeded (the caller then re-bins and re-blends; rare)."""
     dev = depth.device
     P = radius.numel()
     key = (dev.index, P, int(W), int(H))
@@ -242,11 +249,7 @@ def _bin_nosync(uv_like: Tensor, uv_stride: int, depth: Tensor, radius: Tensor, 
     tile_range = torch.empty(n_tiles, 2, dtype=torch.int32, device=dev)
     with torch.cuda.device(dev):
         stream = _stream(dev)
-        offsets = torch.empty(P, dtype=torch.int32, device=dev)
-        total = torch.empty(1, dtype=torch.int32, device=dev)
-        ws_bytes = lib.pxb_binning_workspace_bytes(P, cap, int(W), int(H))
-        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-        launch("pxb_tile_scan", P, _p(tiles), _p(offsets), _p(total), _p(ws), ws_bytes, stream)
+        total, ws_p, ws_p_bytes = _prepare(depth, radius, tiles, stream)
         n_host = _PINNED.get(dev.index)
         if n_host is None:
             n_host = _PINNED[dev.index] = torch.zeros(1, dtype=torch.int32).pin_memory()
@@ -254,8 +257,10 @@ def _bin_nosync(uv_like: Tensor, uv_stride: int, depth: Tensor, radius: Tensor, 
         ev = torch.cuda.Event()
         ev.record()
         idx_sorted = torch.empty(cap, dtype=torch.int32, device=dev)
-        launch("pxb_sort_gaussian_dev", P, cap, _p(total), _p(uv_like), uv_stride, _p(depth), _p(radius), _p(tiles),
-               _p(offsets), int(W), int(H), _p(idx_sorted), _p(tile_range), _p(ws), ws_bytes, stream)
+        ws_n_bytes = lib.pxb_bin_sort_workspace_bytes(cap, int(W), int(H))
+        ws_n = torch.empty(ws_n_bytes, dtype=torch.uint8, device=dev)
+        launch("pxb_sort_gaussian", P, cap, _p(total), _p(uv_like), uv_stride, _p(depth), _p(radius), _p(tiles), int(W),
+               int(H), _p(idx_sorted), _p(tile_range), _p(None), _p(ws_p), ws_p_bytes, _p(ws_n), ws_n_bytes, stream)
 
     def check():
         ev.synchronize()

@@ -43,6 +43,7 @@ def test_pure_host_entry_points():
     from pointrix_b200 import _lib
 
     assert [_lib.lib.pxb_record_stride(c) for c in (1, 2, 3, 6, 7, 10, 18, 26, 27)] == [8, 8, 12, 12, 16, 16, 24, 32, -1]
-    a = _lib.lib.pxb_binning_workspace_bytes(1000, 10000, 1920, 1080)
-    b = _lib.lib.pxb_binning_workspace_bytes(1000, 20000, 1920, 1080)
+    a = _lib.lib.pxb_bin_sort_workspace_bytes(10000, 1920, 1080)
+    b = _lib.lib.pxb_bin_sort_workspace_bytes(20000, 1920, 1080)
     assert 0 < a < b
+    assert 0 < _lib.lib.pxb_bin_prepare_workspace_bytes(1000) < _lib.lib.pxb_bin_prepare_workspace_bytes(100000)
