@@ -34,6 +34,30 @@ __device__ __forceinline__ void thread_pixel(int& lx, int& ly) {
     ly = ((w >> 1) << 2) | (l >> 3);
 }
 
+// Which of the CTA's eight 8x4 pixel blocks can a Gaussian touch at all?  A pixel passes the
+// reference's skip rules only if op*exp(power) >= 1/255, i.e. q(d) = A dx^2 + 2B dx dy + C dy^2 <= 2 ln(255 op);
+// the bounding box of that ellipse (half extents sqrt(k C/det), sqrt(k A/det)), inflated by a safety
+// margin that dwarfs the MUFU approximation error, is tested against each block.  Bit w of the
+// result = block of warp w (thread_pixel).  Conservative: 0xFF whenever the conic is not a
+// proper ellipse; never culls a pixel the exact per-pixel test would blend.
+__device__ __forceinline__ unsigned int block_mask(float u, float v, float A, float B, float C, float op, float X0,
+                                                   float Y0) {
+    if (op < 1.0f / 255.0f) return 0u;  // alpha <= op < 1/255 for every pixel
+    const float det = A * C - B * B;
+    if (!(det > 0.f) || !(A > 0.f) || !(C > 0.f)) return 0xFFu;
+    const float k = 2.02f * __logf(255.0f * op) + 0.02f;
+    const float inv = 1.0f / det;
+    const float hx = sqrtf(k * C * inv) + 0.51f, hy = sqrtf(k * A * inv) + 0.51f;
+    if (!(hx == hx) || !(hy == hy)) return 0xFFu;
+    const float xl = u - hx - X0, xh = u + hx - X0, yl = v - hy - Y0, yh = v + hy - Y0;  // tile-local
+    const unsigned int mx = ((xl <= 7.f && xh >= 0.f) ? 1u : 0u) | ((xl <= 15.f && xh >= 8.f) ? 2u : 0u);
+    unsigned int m = 0;
+#pragma unroll
+    for (int by = 0; by < 4; by++)
+        if (yl <= (float)(4 * by + 3) && yh >= (float)(4 * by)) m |= mx << (2 * by);
+    return m;
+}
+
 // cooperative gather of up to kBatch records into shared memory.
 // Thread t copies float4 number t, t+256, ... of the flattened [kBatch][S/4] set.
 template <int S>
@@ -61,6 +85,7 @@ blend_fwd_kernel(const float* __restrict__ rec, const int* __restrict__ idx_sort
     extern __shared__ __align__(16) float sm_f[];
     float* sm_rec = sm_f;
     int* sm_id = reinterpret_cast<int*>(sm_f + kBatch * S);
+    unsigned char* sm_mask = reinterpret_cast<unsigned char*>(sm_id + kBatch);
     const int tile = blockIdx.y * gx + blockIdx.x;
     int lx, ly;
     thread_pixel(lx, ly);
@@ -71,40 +96,55 @@ blend_fwd_kernel(const float* __restrict__ rec, const int* __restrict__ idx_sort
     const int2 range = tile_range[tile];
     int todo = range.y - range.x;
     float T = 1.0f;
-    int contributor = 0, last = 0;
+    int last = 0;
     float F[CH];
 #pragma unroll
     for (int k = 0; k < CH; k++) F[k] = 0.f;
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const float X0 = (float)(blockIdx.x * PXB_TILE), Y0 = (float)(blockIdx.y * PXB_TILE);
 
     for (int base = 0; todo > 0; base += kBatch, todo -= kBatch) {
         if (__syncthreads_count(done) == kBlendThreads) break;
         const int n = min(kBatch, todo);
         stage_records<S>(sm_rec, sm_id, rec, idx_sorted + range.x + base, n);
         __syncthreads();
-        if (__all_sync(0xffffffffu, done)) continue;  // whole warp saturated: only helps staging
-        for (int j = 0; !done && j < n; j++) {
-            contributor++;
-            const float4 r0 = *reinterpret_cast<const float4*>(sm_rec + j * S);      // u v A B
-            const float4 r1 = *reinterpret_cast<const float4*>(sm_rec + j * S + 4);  // C op f0 f1
-            const float dx = __fadd_rn(r0.x, -pxf), dy = __fadd_rn(r0.y, -pyf);
-            const float power = blend_power(dx, dy, r0.z, r0.w, r1.x);
-            if (power > 0.f) continue;
-            const float alpha = fmin_nn(__fmul_rn(r1.y, blend_G(power)), 0.99f);
-            if (alpha < 1.0f / 255.0f) continue;
-            const float next_T = __fmul_rn(T, __fadd_rn(-alpha, 1.0f));
-            if (next_T < 0.0001f) { done = true; continue; }
-            F[0] = __fmaf_rn(T, __fmul_rn(alpha, r1.z), F[0]);
-            if (CH > 1) F[1] = __fmaf_rn(T, __fmul_rn(alpha, r1.w), F[1]);
+        if ((int)threadIdx.x < n) {
+            const float4 r0 = *reinterpret_cast<const float4*>(sm_rec + threadIdx.x * S);
+            const float2 r1 = *reinterpret_cast<const float2*>(sm_rec + threadIdx.x * S + 4);
+            sm_mask[threadIdx.x] = (unsigned char)block_mask(r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, X0, Y0);
+        }
+        __syncthreads();
+        if (__all_sync(0xffffffffu, done)) continue;  // whole warp saturated: it only helps staging
+        for (int c0 = 0; c0 < n; c0 += 32) {
+            const int jj = c0 + (int)lane;
+            unsigned int m = __ballot_sync(0xffffffffu, jj < n && ((sm_mask[jj] >> warp) & 1u));
+            while (m) {
+                const int j = c0 + __ffs(m) - 1;
+                m &= m - 1;
+                if (done) continue;
+                const float4 r0 = *reinterpret_cast<const float4*>(sm_rec + j * S);      // u v A B
+                const float4 r1 = *reinterpret_cast<const float4*>(sm_rec + j * S + 4);  // C op f0 f1
+                const float dx = __fadd_rn(r0.x, -pxf), dy = __fadd_rn(r0.y, -pyf);
+                const float power = blend_power(dx, dy, r0.z, r0.w, r1.x);
+                if (power > 0.f) continue;
+                const float alpha = fmin_nn(__fmul_rn(r1.y, blend_G(power)), 0.99f);
+                if (alpha < 1.0f / 255.0f) continue;
+                const float next_T = __fmul_rn(T, __fadd_rn(-alpha, 1.0f));
+                if (next_T < 0.0001f) { done = true; continue; }
+                F[0] = __fmaf_rn(T, __fmul_rn(alpha, r1.z), F[0]);
+                if (CH > 1) F[1] = __fmaf_rn(T, __fmul_rn(alpha, r1.w), F[1]);
 #pragma unroll
-            for (int q = 2; q < CH; q += 4) {
-                const float4 rf = *reinterpret_cast<const float4*>(sm_rec + j * S + 6 + q);
-                F[q] = __fmaf_rn(T, __fmul_rn(alpha, rf.x), F[q]);
-                if (q + 1 < CH) F[q + 1] = __fmaf_rn(T, __fmul_rn(alpha, rf.y), F[q + 1]);
-                if (q + 2 < CH) F[q + 2] = __fmaf_rn(T, __fmul_rn(alpha, rf.z), F[q + 2]);
-                if (q + 3 < CH) F[q + 3] = __fmaf_rn(T, __fmul_rn(alpha, rf.w), F[q + 3]);
+                for (int q = 2; q < CH; q += 4) {
+                    const float4 rf = *reinterpret_cast<const float4*>(sm_rec + j * S + 6 + q);
+                    F[q] = __fmaf_rn(T, __fmul_rn(alpha, rf.x), F[q]);
+                    if (q + 1 < CH) F[q + 1] = __fmaf_rn(T, __fmul_rn(alpha, rf.y), F[q + 1]);
+                    if (q + 2 < CH) F[q + 2] = __fmaf_rn(T, __fmul_rn(alpha, rf.z), F[q + 2]);
+                    if (q + 3 < CH) F[q + 3] = __fmaf_rn(T, __fmul_rn(alpha, rf.w), F[q + 3]);
+                }
+                T = next_T;
+                last = base + j + 1;  // 1-based list position of the last blended Gaussian (ncontrib)
             }
-            T = next_T;
-            last = contributor;
+            if (__all_sync(0xffffffffu, done)) break;
         }
     }
     if (inside) {
@@ -152,6 +192,7 @@ blend_bwd_kernel(const float* __restrict__ rec, const int* __restrict__ idx_sort
     extern __shared__ __align__(16) float sm_f[];
     float* sm_rec = sm_f;
     int* sm_id = reinterpret_cast<int*>(sm_f + kBatch * S);
+    unsigned char* sm_mask = reinterpret_cast<unsigned char*>(sm_id + kBatch);
     const int tile = blockIdx.y * gx + blockIdx.x;
     int lx, ly;
     thread_pixel(lx, ly);
@@ -160,10 +201,9 @@ blend_bwd_kernel(const float* __restrict__ rec, const int* __restrict__ idx_sort
     const bool inside = pxi < W && pyi < H;
     const size_t pix = (size_t)pyi * W + pxi;
     const int2 range = tile_range[tile];
-    int todo = range.y - range.x;
+    const int count = range.y - range.x;
     const float T_final = inside ? final_T[pix] : 0.f;
     float T = T_final;
-    int contributor = todo;
     const int last = inside ? ncontrib[pix] : 0;
     float accum[CH], dpix[CH], lastf[CH];
     float bg_dot = 0.f;
@@ -174,14 +214,23 @@ blend_bwd_kernel(const float* __restrict__ rec, const int* __restrict__ idx_sort
         bg_dot += bg * dpix[k];
     }
     float last_alpha = 0.f;
-    // the deepest contributor of any pixel in this warp bounds the warp's work
+    // the deepest contributor of any pixel of the CTA / of this warp bounds the work: list entries
+    // at positions >= that bound were never blended by these pixels
     const int warp_last = __reduce_max_sync(0xffffffffu, last);
-    const unsigned lane = threadIdx.x & 31u;
+    __shared__ int s_cta_last;
+    if (threadIdx.x == 0) s_cta_last = 0;
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) atomicMax(&s_cta_last, warp_last);
+    __syncthreads();
+    const int cta_last = s_cta_last;
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const float X0 = (float)(blockIdx.x * PXB_TILE), Y0 = (float)(blockIdx.y * PXB_TILE);
 
-    for (int base = 0; todo > 0; base += kBatch, todo -= kBatch) {
+    // walk the list back to front starting at the CTA's deepest contributor
+    for (int top = min(count, cta_last); top > 0; top -= kBatch) {
         __syncthreads();
-        const int n = min(kBatch, todo);
-        // batch b holds list entries range.y-1-base-j (back to front)
+        const int n = min(kBatch, top);
+        // entry j of the batch is list position top-1-j
         {
             constexpr int Q = S / 4;
 #pragma unroll
@@ -189,63 +238,71 @@ blend_bwd_kernel(const float* __restrict__ rec, const int* __restrict__ idx_sort
                 const int f = it * kBlendThreads + threadIdx.x;
                 const int j = f / Q, q = f - j * Q;
                 if (j < n) {
-                    const int g = idx_sorted[range.y - 1 - base - j];
+                    const int g = idx_sorted[range.x + top - 1 - j];
                     if (q == 0) sm_id[j] = g;
                     reinterpret_cast<float4*>(sm_rec)[f] = __ldg(reinterpret_cast<const float4*>(rec + (size_t)g * S) + q);
                 }
             }
         }
         __syncthreads();
-        // entries with index >= warp_last contribute to no pixel of this warp
-        int j0 = 0;
-        if (contributor - warp_last > 0) j0 = min(n, contributor - warp_last);
-        contributor -= j0;
-        for (int j = j0; j < n; j++) {
-            contributor--;
-            bool valid = contributor < last;
-            float dx = 0.f, dy = 0.f, G = 0.f, alpha = 0.f;
-            float4 r0, r1;
-            r0 = *reinterpret_cast<const float4*>(sm_rec + j * S);
-            r1 = *reinterpret_cast<const float4*>(sm_rec + j * S + 4);
-            if (valid) {
-                dx = __fadd_rn(r0.x, -pxf); dy = __fadd_rn(r0.y, -pyf);
-                const float power = blend_power(dx, dy, r0.z, r0.w, r1.x);
-                G = blend_G(power);
-                alpha = fmin_nn(__fmul_rn(r1.y, G), 0.99f);
-                valid = !(power > 0.f) && !(alpha < 1.0f / 255.0f);
-            }
-            if (!__any_sync(0xffffffffu, valid)) continue;
-            float v[NVP];
-#pragma unroll
-            for (int k = 0; k < NVP; k++) v[k] = 0.f;
-            if (valid) {
-                T = __fdividef(T, 1.f - alpha);
-                const float w = alpha * T;
-                float dL_dalpha = 0.f;
-#pragma unroll
-                for (int k = 0; k < CH; k++) {
-                    const float f = sm_rec[j * S + 6 + k];
-                    accum[k] = last_alpha * lastf[k] + (1.f - last_alpha) * accum[k];
-                    lastf[k] = f;
-                    dL_dalpha += (f - accum[k]) * dpix[k];
-                    v[6 + k] = w * dpix[k];
+        if ((int)threadIdx.x < n) {
+            const float4 r0 = *reinterpret_cast<const float4*>(sm_rec + threadIdx.x * S);
+            const float2 r1 = *reinterpret_cast<const float2*>(sm_rec + threadIdx.x * S + 4);
+            sm_mask[threadIdx.x] = (unsigned char)block_mask(r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, X0, Y0);
+        }
+        __syncthreads();
+        for (int c0 = 0; c0 < n; c0 += 32) {
+            const int jj = c0 + (int)lane;
+            // positions >= warp_last contribute to no pixel of this warp
+            unsigned int m = __ballot_sync(0xffffffffu, jj < n && (top - 1 - jj) < warp_last && ((sm_mask[jj] >> warp) & 1u));
+            while (m) {
+                const int j = c0 + __ffs(m) - 1;
+                m &= m - 1;
+                const int pos = top - 1 - j;  // list position of this entry
+                bool valid = pos < last;
+                float dx = 0.f, dy = 0.f, G = 0.f, alpha = 0.f;
+                const float4 r0 = *reinterpret_cast<const float4*>(sm_rec + j * S);
+                const float4 r1 = *reinterpret_cast<const float4*>(sm_rec + j * S + 4);
+                if (valid) {
+                    dx = __fadd_rn(r0.x, -pxf); dy = __fadd_rn(r0.y, -pyf);
+                    const float power = blend_power(dx, dy, r0.z, r0.w, r1.x);
+                    G = blend_G(power);
+                    alpha = fmin_nn(__fmul_rn(r1.y, G), 0.99f);
+                    valid = !(power > 0.f) && !(alpha < 1.0f / 255.0f);
                 }
-                dL_dalpha *= T;
-                last_alpha = alpha;
-                dL_dalpha += (-T_final / (1.f - alpha)) * bg_dot;
-                const float dL_dG = r1.y * dL_dalpha;
-                const float gdx = G * dx, gdy = G * dy;
-                v[0] = dL_dG * (-gdx * r0.z - gdy * r0.w);
-                v[1] = dL_dG * (-gdy * r1.x - gdx * r0.w);
-                v[2] = -0.5f * gdx * dx * dL_dG;
-                v[3] = -gdx * dy * dL_dG;
-                v[4] = -0.5f * gdy * dy * dL_dG;
-                v[5] = G * dL_dalpha;
+                if (!__any_sync(0xffffffffu, valid)) continue;
+                float v[NVP];
+#pragma unroll
+                for (int k = 0; k < NVP; k++) v[k] = 0.f;
+                if (valid) {
+                    T = __fdividef(T, 1.f - alpha);
+                    const float w = alpha * T;
+                    float dL_dalpha = 0.f;
+#pragma unroll
+                    for (int k = 0; k < CH; k++) {
+                        const float f = sm_rec[j * S + 6 + k];
+                        accum[k] = last_alpha * lastf[k] + (1.f - last_alpha) * accum[k];
+                        lastf[k] = f;
+                        dL_dalpha += (f - accum[k]) * dpix[k];
+                        v[6 + k] = w * dpix[k];
+                    }
+                    dL_dalpha *= T;
+                    last_alpha = alpha;
+                    dL_dalpha += (-T_final / (1.f - alpha)) * bg_dot;
+                    const float dL_dG = r1.y * dL_dalpha;
+                    const float gdx = G * dx, gdy = G * dy;
+                    v[0] = dL_dG * (-gdx * r0.z - gdy * r0.w);
+                    v[1] = dL_dG * (-gdy * r1.x - gdx * r0.w);
+                    v[2] = -0.5f * gdx * dx * dL_dG;
+                    v[3] = -gdx * dy * dL_dG;
+                    v[4] = -0.5f * gdy * dy * dL_dG;
+                    v[5] = G * dL_dalpha;
+                }
+                warp_reduce_vec<NVP>(v);
+                constexpr int REP = 32 / NVP;
+                const int idx = lane / REP;
+                if ((lane % REP) == 0 && idx < 6 + C && v[0] != 0.f) atomicAdd(grec + (size_t)sm_id[j] * S + idx, v[0]);
             }
-            warp_reduce_vec<NVP>(v);
-            constexpr int REP = 32 / NVP;
-            const int idx = lane / REP;
-            if ((lane % REP) == 0 && idx < 6 + C && v[0] != 0.f) atomicAdd(grec + (size_t)sm_id[j] * S + idx, v[0]);
         }
     }
 }
@@ -286,7 +343,7 @@ template <int CH, int S>
 static int launch_fwd(const float* rec, const int* idx_sorted, const int* tile_range, float bg, int C, int W, int H,
                       float* final_T, int* ncontrib, float* out, cudaStream_t s) {
     const int gx = (W + PXB_TILE - 1) / PXB_TILE, gy = (H + PXB_TILE - 1) / PXB_TILE;
-    const size_t smem = (size_t)kBatch * S * 4 + kBatch * 4;
+    const size_t smem = (size_t)kBatch * S * 4 + kBatch * 4 + kBatch;
     static bool attr = false;
     if (!attr && smem > 48 * 1024) {
         PXB_CUDA_OK(cudaFuncSetAttribute(blend_fwd_kernel<CH, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -301,7 +358,7 @@ template <int CH, int S, int NVP>
 static int launch_bwd(const float* rec, const int* idx_sorted, const int* tile_range, float bg, int C, int W, int H,
                       const float* final_T, const int* ncontrib, const float* dL_dout, float* grec, cudaStream_t s) {
     const int gx = (W + PXB_TILE - 1) / PXB_TILE, gy = (H + PXB_TILE - 1) / PXB_TILE;
-    const size_t smem = (size_t)kBatch * S * 4 + kBatch * 4;
+    const size_t smem = (size_t)kBatch * S * 4 + kBatch * 4 + kBatch;
     static bool attr = false;
     if (!attr && smem > 48 * 1024) {
         PXB_CUDA_OK(cudaFuncSetAttribute(blend_bwd_kernel<CH, S, NVP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
