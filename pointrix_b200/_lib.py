@@ -8,7 +8,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpointrix_b200.so")
+# PXB_LIBRARY: developer override (e.g. the -DPXB_STATS build); never a fallback
+LIB_PATH = os.environ.get("PXB_LIBRARY") or os.path.join(_HERE, "libpointrix_b200.so")
 
 ERRORS = {-1: "bad argument", -2: "unsupported configuration", -3: "workspace too small", -4: "pointer not 16-byte aligned"}
 

@@ -58,6 +58,13 @@ __device__ __forceinline__ unsigned int block_mask(float u, float v, float A, fl
     return m;
 }
 
+#ifdef PXB_STATS
+__device__ unsigned long long g_blend_stats[8];
+#define PXB_STAT(i, v) do { if ((threadIdx.x & 31) == 0) atomicAdd(&g_blend_stats[i], (unsigned long long)(v)); } while (0)
+#else
+#define PXB_STAT(i, v) do { } while (0)
+#endif
+
 // cooperative gather of up to kBatch records into shared memory.
 // Thread t copies float4 number t, t+256, ... of the flattened [kBatch][S/4] set.
 template <int S>
@@ -118,6 +125,7 @@ blend_fwd_kernel(const float* __restrict__ rec, const int* __restrict__ idx_sort
         for (int c0 = 0; c0 < n; c0 += 32) {
             const int jj = c0 + (int)lane;
             unsigned int m = __ballot_sync(0xffffffffu, jj < n && ((sm_mask[jj] >> warp) & 1u));
+            PXB_STAT(5, __popc(m));
             while (m) {
                 const int j = c0 + __ffs(m) - 1;
                 m &= m - 1;
@@ -157,42 +165,41 @@ blend_fwd_kernel(const float* __restrict__ rec, const int* __restrict__ idx_sort
     }
 }
 
-// Sum NV per-lane values across the warp.  v[] is padded to NVP (power of two
-// >= NV, <= 32).  On return lane L holds in v[0] the total of value index
-// L / (32/NVP): each butterfly stage exchanges half of the remaining values.
-template <int NVP>
-__device__ __forceinline__ void warp_reduce_vec(float (&v)[NVP]) {
-    const unsigned lane = threadIdx.x & 31u;
-    int n = NVP;
-#pragma unroll
-    for (int step = 16; step >= 1; step >>= 1) {
-        if (n > 1) {
-            const int half = n / 2;
-            const bool upper = (lane & step) != 0;
-#pragma unroll
-            for (int k = 0; k < NVP / 2; k++) {
-                if (k < half) {
-                    const float send = upper ? v[k] : v[k + half];
-                    const float keep = upper ? v[k + half] : v[k];
-                    v[k] = keep + __shfl_xor_sync(0xffffffffu, send, step);
-                }
-            }
-            n = half;
-        } else {
-            v[0] += __shfl_xor_sync(0xffffffffu, v[0], step);
-        }
-    }
-}
+// ---------------------------------------------------------------------------
+// Backward.  Two phases per warp:
+//   phase 1 (lane = pixel): back-to-front replay of the warp's 8x4 pixel block with the reference's
+//     skip rules; for every (pixel, Gaussian) pair that was blended it produces the two scalars all
+//     gradients are linear in,
+//         q = G * dL/dalpha        w = alpha * T
+//     and parks them in a warp-private shared-memory slot (row = Gaussian, column = pixel);
+//   phase 2 (lane = Gaussian): when kSlots Gaussians are parked, lane pair (g, g+16) walks the 32
+//     pixels of Gaussian g's row and accumulates the moments
+//         Q0 = sum q, Q1 = sum q dx, Q2 = sum q dy, Q3 = sum q dx^2, Q4 = sum q dx dy, Q5 = sum q dy^2,
+//         F_k = sum w dL/dpix_k
+//     in registers, from which
+//         dL/du = -op (A Q1 + B Q2)   dL/dv = -op (C Q2 + B Q1)   dL/dA = -op Q3 / 2   dL/dB = -op Q4
+//         dL/dC = -op Q5 / 2          dL/dop = Q0                  dL/df_k = F_k
+//     (the reference's per-pair expressions, alpha_blending.cu:206-243, summed over pixels).
+// There is no cross-lane reduction tree: the reference issues 6+C scalar atomics per (pixel,
+// Gaussian); this kernel issues ceil((6+C)/4) 16-byte vector atomics per (8x4 block, Gaussian) and
+// spends one shuffle per value per 16 Gaussians.
+// ---------------------------------------------------------------------------
+constexpr int kSlots = 16;
+constexpr int kSlotPitch = 33;  // float2 units: conflict-free row (phase 1) and column (phase 2) access
 
-template <int CH, int S, int NVP>
+template <int CH, int S>
 __global__ void __launch_bounds__(kBlendThreads)
 blend_bwd_kernel(const float* __restrict__ rec, const int* __restrict__ idx_sorted, const int2* __restrict__ tile_range,
                  float bg, int C, int W, int H, int gx, const float* __restrict__ final_T,
                  const int* __restrict__ ncontrib, const float* __restrict__ dL_dout, float* __restrict__ grec) {
+    constexpr int CHP = (CH + 3) & ~3;  // dL/dpix row padded to float4s
+    constexpr int NW = kBlendThreads / 32;
     extern __shared__ __align__(16) float sm_f[];
-    float* sm_rec = sm_f;
-    int* sm_id = reinterpret_cast<int*>(sm_f + kBatch * S);
-    unsigned char* sm_mask = reinterpret_cast<unsigned char*>(sm_id + kBatch);
+    float* sm_rec = sm_f;                                               // [kBatch][S]
+    float* sm_dpix = sm_rec + kBatch * S;                               // [NW][32][CHP]
+    float2* sm_slot = reinterpret_cast<float2*>(sm_dpix + NW * 32 * CHP);  // [NW][kSlots][kSlotPitch]
+    int* sm_id = reinterpret_cast<int*>(sm_slot + NW * kSlots * kSlotPitch);  // [kBatch]
+    unsigned char* sm_mask = reinterpret_cast<unsigned char*>(sm_id + kBatch);  // [kBatch]
     const int tile = blockIdx.y * gx + blockIdx.x;
     int lx, ly;
     thread_pixel(lx, ly);
@@ -202,16 +209,19 @@ blend_bwd_kernel(const float* __restrict__ rec, const int* __restrict__ idx_sort
     const size_t pix = (size_t)pyi * W + pxi;
     const int2 range = tile_range[tile];
     const int count = range.y - range.x;
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     const float T_final = inside ? final_T[pix] : 0.f;
     float T = T_final;
     const int last = inside ? ncontrib[pix] : 0;
     float accum[CH], dpix[CH], lastf[CH];
     float bg_dot = 0.f;
+    float* my_dpix = sm_dpix + (warp * 32 + lane) * CHP;
 #pragma unroll
     for (int k = 0; k < CH; k++) {
         accum[k] = 0.f; lastf[k] = 0.f;
         dpix[k] = (inside && k < C) ? dL_dout[(size_t)k * H * W + pix] : 0.f;
         bg_dot += bg * dpix[k];
+        my_dpix[k] = dpix[k];
     }
     float last_alpha = 0.f;
     // the deepest contributor of any pixel of the CTA / of this warp bounds the work: list entries
@@ -220,11 +230,76 @@ blend_bwd_kernel(const float* __restrict__ rec, const int* __restrict__ idx_sort
     __shared__ int s_cta_last;
     if (threadIdx.x == 0) s_cta_last = 0;
     __syncthreads();
-    if ((threadIdx.x & 31) == 0) atomicMax(&s_cta_last, warp_last);
+    if (lane == 0) atomicMax(&s_cta_last, warp_last);
     __syncthreads();
     const int cta_last = s_cta_last;
-    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     const float X0 = (float)(blockIdx.x * PXB_TILE), Y0 = (float)(blockIdx.y * PXB_TILE);
+
+    // phase-2 role of this lane: Gaussian slot (lane & 15), pixel half (lane >> 4) = rows 2h, 2h+1 of the block
+    float2* slots = sm_slot + warp * (kSlots * kSlotPitch);
+    const float* wdpix = sm_dpix + warp * 32 * CHP;
+    const int my_slot = lane & 15, my_half = lane >> 4;
+    const float bx = X0 + (float)((warp & 1) << 3);                       // block origin (pixel centres are integers)
+    const float by = Y0 + (float)(((warp >> 1) << 2) + 2 * my_half);
+    int nslot = 0;   // warp-uniform
+    int my_j = 0;    // batch entry parked in my_slot
+
+    auto flush = [&](int n) {
+        __syncwarp();
+        const float* r = sm_rec + my_j * S;
+        const float4 r0 = *reinterpret_cast<const float4*>(r);      // u v A B
+        const float2 r1 = *reinterpret_cast<const float2*>(r + 4);  // C op
+        const float ub = r0.x - bx, vb = r0.y - by;
+        float Q0 = 0.f, Q1 = 0.f, Q2 = 0.f, Q3 = 0.f, Q4 = 0.f, Q5 = 0.f;
+        float Fk[CH];
+#pragma unroll
+        for (int k = 0; k < CH; k++) Fk[k] = 0.f;
+        const float2* row = slots + my_slot * kSlotPitch + 16 * my_half;
+        const float* dp = wdpix + 16 * my_half * CHP;
+#pragma unroll
+        for (int i = 0; i < 16; i++) {
+            const float2 qw = row[i];
+            const float dx = ub - (float)(i & 7), dy = vb - (float)(i >> 3);
+            const float qdx = qw.x * dx, qdy = qw.x * dy;
+            Q0 += qw.x; Q1 += qdx; Q2 += qdy;
+            Q3 = fmaf(qdx, dx, Q3); Q4 = fmaf(qdx, dy, Q4); Q5 = fmaf(qdy, dy, Q5);
+#pragma unroll
+            for (int k4 = 0; k4 < CHP; k4 += 4) {
+                const float4 d4 = *reinterpret_cast<const float4*>(dp + i * CHP + k4);
+                Fk[k4] = fmaf(qw.y, d4.x, Fk[k4]);
+                if (k4 + 1 < CH) Fk[k4 + 1] = fmaf(qw.y, d4.y, Fk[k4 + 1]);
+                if (k4 + 2 < CH) Fk[k4 + 2] = fmaf(qw.y, d4.z, Fk[k4 + 2]);
+                if (k4 + 3 < CH) Fk[k4 + 3] = fmaf(qw.y, d4.w, Fk[k4 + 3]);
+            }
+        }
+        Q0 += __shfl_xor_sync(0xffffffffu, Q0, 16); Q1 += __shfl_xor_sync(0xffffffffu, Q1, 16);
+        Q2 += __shfl_xor_sync(0xffffffffu, Q2, 16); Q3 += __shfl_xor_sync(0xffffffffu, Q3, 16);
+        Q4 += __shfl_xor_sync(0xffffffffu, Q4, 16); Q5 += __shfl_xor_sync(0xffffffffu, Q5, 16);
+#pragma unroll
+        for (int k = 0; k < CH; k++) Fk[k] += __shfl_xor_sync(0xffffffffu, Fk[k], 16);
+        if ((int)lane < n) {
+            const float nop = -r1.y;
+            float g[S];
+            g[0] = nop * fmaf(r0.z, Q1, r0.w * Q2);
+            g[1] = nop * fmaf(r1.x, Q2, r0.w * Q1);
+            g[2] = 0.5f * nop * Q3;
+            g[3] = nop * Q4;
+            g[4] = 0.5f * nop * Q5;
+            g[5] = Q0;
+#pragma unroll
+            for (int k = 0; k < S - 6; k++) g[6 + k] = (k < CH) ? Fk[k] : 0.f;
+            float* dst = grec + (size_t)sm_id[my_j] * S;
+#pragma unroll
+            for (int q4 = 0; q4 < S; q4 += 4) {
+                if (q4 + 1 >= 6 + CH) {          // one live value left in this float4
+                    if (q4 < 6 + CH) atomicAdd(dst + q4, g[q4]);
+                } else if (q4 < 6 + CH) {
+                    atomicAdd(reinterpret_cast<float4*>(dst + q4), make_float4(g[q4], g[q4 + 1], g[q4 + 2], g[q4 + 3]));
+                }
+            }
+        }
+        __syncwarp();
+    };
 
     // walk the list back to front starting at the CTA's deepest contributor
     for (int top = min(count, cta_last); top > 0; top -= kBatch) {
@@ -255,54 +330,57 @@ blend_bwd_kernel(const float* __restrict__ rec, const int* __restrict__ idx_sort
             const int jj = c0 + (int)lane;
             // positions >= warp_last contribute to no pixel of this warp
             unsigned int m = __ballot_sync(0xffffffffu, jj < n && (top - 1 - jj) < warp_last && ((sm_mask[jj] >> warp) & 1u));
+            PXB_STAT(0, __popc(m));
             while (m) {
                 const int j = c0 + __ffs(m) - 1;
                 m &= m - 1;
                 const int pos = top - 1 - j;  // list position of this entry
                 bool valid = pos < last;
-                float dx = 0.f, dy = 0.f, G = 0.f, alpha = 0.f;
+                float G = 0.f, alpha = 0.f;
                 const float4 r0 = *reinterpret_cast<const float4*>(sm_rec + j * S);
                 const float4 r1 = *reinterpret_cast<const float4*>(sm_rec + j * S + 4);
                 if (valid) {
-                    dx = __fadd_rn(r0.x, -pxf); dy = __fadd_rn(r0.y, -pyf);
+                    const float dx = __fadd_rn(r0.x, -pxf), dy = __fadd_rn(r0.y, -pyf);
                     const float power = blend_power(dx, dy, r0.z, r0.w, r1.x);
                     G = blend_G(power);
                     alpha = fmin_nn(__fmul_rn(r1.y, G), 0.99f);
                     valid = !(power > 0.f) && !(alpha < 1.0f / 255.0f);
                 }
-                if (!__any_sync(0xffffffffu, valid)) continue;
-                float v[NVP];
-#pragma unroll
-                for (int k = 0; k < NVP; k++) v[k] = 0.f;
+                const unsigned int vm = __ballot_sync(0xffffffffu, valid);
+                if (vm == 0u) continue;
+                PXB_STAT(1, 1); PXB_STAT(2, __popc(vm));
+                float2 qw = make_float2(0.f, 0.f);
                 if (valid) {
-                    T = __fdividef(T, 1.f - alpha);
-                    const float w = alpha * T;
+                    const float ra = __fdividef(1.f, 1.f - alpha);
+                    T = T * ra;
+                    qw.y = alpha * T;
                     float dL_dalpha = 0.f;
 #pragma unroll
                     for (int k = 0; k < CH; k++) {
-                        const float f = sm_rec[j * S + 6 + k];
+                        const float f = (k == 0) ? r1.z : (k == 1) ? r1.w : sm_rec[j * S + 6 + k];
                         accum[k] = last_alpha * lastf[k] + (1.f - last_alpha) * accum[k];
                         lastf[k] = f;
                         dL_dalpha += (f - accum[k]) * dpix[k];
-                        v[6 + k] = w * dpix[k];
                     }
                     dL_dalpha *= T;
                     last_alpha = alpha;
-                    dL_dalpha += (-T_final / (1.f - alpha)) * bg_dot;
-                    const float dL_dG = r1.y * dL_dalpha;
-                    const float gdx = G * dx, gdy = G * dy;
-                    v[0] = dL_dG * (-gdx * r0.z - gdy * r0.w);
-                    v[1] = dL_dG * (-gdy * r1.x - gdx * r0.w);
-                    v[2] = -0.5f * gdx * dx * dL_dG;
-                    v[3] = -gdx * dy * dL_dG;
-                    v[4] = -0.5f * gdy * dy * dL_dG;
-                    v[5] = G * dL_dalpha;
+                    dL_dalpha += (-T_final * ra) * bg_dot;
+                    qw.x = G * dL_dalpha;
                 }
-                warp_reduce_vec<NVP>(v);
-                constexpr int REP = 32 / NVP;
-                const int idx = lane / REP;
-                if ((lane % REP) == 0 && idx < 6 + C && v[0] != 0.f) atomicAdd(grec + (size_t)sm_id[j] * S + idx, v[0]);
+                slots[nslot * kSlotPitch + lane] = qw;
+                if (my_slot == nslot) my_j = j;
+                nslot++;
+                if (nslot == kSlots) {
+                    PXB_STAT(3, 1);
+                    flush(kSlots);
+                    nslot = 0;
+                }
             }
+        }
+        if (nslot) {  // the batch buffer is about to be restaged: drain
+            PXB_STAT(3, 1); PXB_STAT(4, nslot);
+            flush(nslot);
+            nslot = 0;
         }
     }
 }
@@ -354,20 +432,40 @@ static int launch_fwd(const float* rec, const int* idx_sorted, const int* tile_r
     return (int)cudaGetLastError();
 }
 
-template <int CH, int S, int NVP>
+template <int CH, int S>
 static int launch_bwd(const float* rec, const int* idx_sorted, const int* tile_range, float bg, int C, int W, int H,
                       const float* final_T, const int* ncontrib, const float* dL_dout, float* grec, cudaStream_t s) {
     const int gx = (W + PXB_TILE - 1) / PXB_TILE, gy = (H + PXB_TILE - 1) / PXB_TILE;
-    const size_t smem = (size_t)kBatch * S * 4 + kBatch * 4 + kBatch;
+    constexpr int CHP = (CH + 3) & ~3, NW = kBlendThreads / 32;
+    const size_t smem = (size_t)(kBatch * S + NW * 32 * CHP + 2 * NW * kSlots * kSlotPitch) * 4 + kBatch * 4 + kBatch;
     static bool attr = false;
     if (!attr && smem > 48 * 1024) {
-        PXB_CUDA_OK(cudaFuncSetAttribute(blend_bwd_kernel<CH, S, NVP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        PXB_CUDA_OK(cudaFuncSetAttribute(blend_bwd_kernel<CH, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr = true;
     }
-    blend_bwd_kernel<CH, S, NVP><<<dim3(gx, gy), kBlendThreads, smem, s>>>(
+    blend_bwd_kernel<CH, S><<<dim3(gx, gy), kBlendThreads, smem, s>>>(
         rec, idx_sorted, (const int2*)tile_range, bg, C, W, H, gx, final_T, ncontrib, dL_dout, grec);
     return (int)cudaGetLastError();
 }
+
+// kernels are instantiated for the exact channel count up to 10 (rgb, rgb+depth, rgb+normal, ... the
+// cfg4 set rgb+depth+normal+flow = 9), then for the two wide record strides
+#define PXB_BLEND_DISPATCH(LAUNCH, ...)                              \
+    switch (C) {                                                     \
+        case 1: return LAUNCH<1, 8>(__VA_ARGS__);                    \
+        case 2: return LAUNCH<2, 8>(__VA_ARGS__);                    \
+        case 3: return LAUNCH<3, 12>(__VA_ARGS__);                   \
+        case 4: return LAUNCH<4, 12>(__VA_ARGS__);                   \
+        case 5: return LAUNCH<5, 12>(__VA_ARGS__);                   \
+        case 6: return LAUNCH<6, 12>(__VA_ARGS__);                   \
+        case 7: return LAUNCH<7, 16>(__VA_ARGS__);                   \
+        case 8: return LAUNCH<8, 16>(__VA_ARGS__);                   \
+        case 9: return LAUNCH<9, 16>(__VA_ARGS__);                   \
+        case 10: return LAUNCH<10, 16>(__VA_ARGS__);                 \
+        default:                                                     \
+            if (C <= 18) return LAUNCH<18, 24>(__VA_ARGS__);         \
+            return LAUNCH<26, 32>(__VA_ARGS__);                      \
+    }
 
 }  // namespace pxb
 
@@ -389,15 +487,9 @@ int pxb_blend_forward(const float* rec, int S, int C, const int* idx_sorted, con
                       int H, float* final_T, int* ncontrib, float* out, void* stream) {
     cudaStream_t s = (cudaStream_t)stream;
     if (W <= 0 || H <= 0) return 0;
+    if (C < 1 || C > PXB_MAX_CHANNELS_PER_PASS || S != pxb_record_stride(C)) return PXB_ERR_BAD_ARG;
     if (((uintptr_t)rec) & 15) return PXB_ERR_ALIGN;
-    switch (S) {
-        case 8: return launch_fwd<2, 8>(rec, idx_sorted, tile_range, bg, C, W, H, final_T, ncontrib, out, s);
-        case 12: return launch_fwd<6, 12>(rec, idx_sorted, tile_range, bg, C, W, H, final_T, ncontrib, out, s);
-        case 16: return launch_fwd<10, 16>(rec, idx_sorted, tile_range, bg, C, W, H, final_T, ncontrib, out, s);
-        case 24: return launch_fwd<18, 24>(rec, idx_sorted, tile_range, bg, C, W, H, final_T, ncontrib, out, s);
-        case 32: return launch_fwd<26, 32>(rec, idx_sorted, tile_range, bg, C, W, H, final_T, ncontrib, out, s);
-    }
-    return PXB_ERR_BAD_ARG;
+    PXB_BLEND_DISPATCH(launch_fwd, rec, idx_sorted, tile_range, bg, C, W, H, final_T, ncontrib, out, s)
 }
 
 int pxb_blend_backward(const float* rec, int S, int C, const int* idx_sorted, const int* tile_range, float bg, int W,
@@ -405,16 +497,19 @@ int pxb_blend_backward(const float* rec, int S, int C, const int* idx_sorted, co
                        void* stream) {
     cudaStream_t s = (cudaStream_t)stream;
     if (W <= 0 || H <= 0) return 0;
+    if (C < 1 || C > PXB_MAX_CHANNELS_PER_PASS || S != pxb_record_stride(C)) return PXB_ERR_BAD_ARG;
     if ((((uintptr_t)rec) | ((uintptr_t)grec)) & 15) return PXB_ERR_ALIGN;
-    switch (S) {
-        case 8: return launch_bwd<2, 8, 8>(rec, idx_sorted, tile_range, bg, C, W, H, final_T, ncontrib, dL_dout, grec, s);
-        case 12: return launch_bwd<6, 12, 16>(rec, idx_sorted, tile_range, bg, C, W, H, final_T, ncontrib, dL_dout, grec, s);
-        case 16: return launch_bwd<10, 16, 16>(rec, idx_sorted, tile_range, bg, C, W, H, final_T, ncontrib, dL_dout, grec, s);
-        case 24: return launch_bwd<18, 24, 32>(rec, idx_sorted, tile_range, bg, C, W, H, final_T, ncontrib, dL_dout, grec, s);
-        case 32: return launch_bwd<26, 32, 32>(rec, idx_sorted, tile_range, bg, C, W, H, final_T, ncontrib, dL_dout, grec, s);
-    }
-    return PXB_ERR_BAD_ARG;
+    PXB_BLEND_DISPATCH(launch_bwd, rec, idx_sorted, tile_range, bg, C, W, H, final_T, ncontrib, dL_dout, grec, s)
 }
+
+#ifdef PXB_STATS
+int pxb_blend_stats(unsigned long long* host8, int reset) {
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(host8, g_blend_stats, sizeof(unsigned long long) * 8);
+    if (reset) { unsigned long long z[8] = {0}; cudaMemcpyToSymbol(g_blend_stats, z, sizeof(z)); }
+    return 0;
+}
+#endif
 
 int pxb_pack_records(int P, const float* uv, const float* conic, const float* opacity, const float* feature, int C,
                      int c0, int cn, int S, float* rec, void* stream) {

@@ -44,15 +44,19 @@ def needs_build() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not needs_build():
+def build(force: bool = False, verbose: bool = False, stats: bool = False) -> str:
+    """stats=True builds the instrumented developer variant (-DPXB_STATS: pair-test counters in the
+    blend kernels) next to the product library; the package never loads it unless PXB_LIBRARY says so."""
+    lib = LIB.replace(".so", "_stats.so") if stats else LIB
+    if not stats and not force and not needs_build():
         return LIB
     objs = []
     procs = []
-    os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
+    bdir = os.path.join(HERE, "build_stats" if stats else "build")
+    os.makedirs(bdir, exist_ok=True)
     for s in SOURCES:
-        o = os.path.join(HERE, "build", s.replace(".cu", ".o"))
-        cmd = [_nvcc(), *NVCC_FLAGS, "-c", os.path.join(HERE, s), "-o", o]
+        o = os.path.join(bdir, s.replace(".cu", ".o"))
+        cmd = [_nvcc(), *NVCC_FLAGS, *(["-DPXB_STATS"] if stats else []), "-c", os.path.join(HERE, s), "-o", o]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
             print(" ".join(cmd))
@@ -66,10 +70,10 @@ def build(force: bool = False, verbose: bool = False) -> str:
         failed |= p.returncode != 0
     if failed:
         raise RuntimeError("nvcc failed")
-    cmd = [_nvcc(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB, *objs]
+    cmd = [_nvcc(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", lib, *objs]
     subprocess.check_call(cmd)
-    return LIB
+    return lib
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))
+    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv, stats="--stats" in sys.argv))
