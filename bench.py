@@ -248,16 +248,25 @@ def main():
     h2d = (16 + 4 + 3) * 4 + host_dimg.numel() * 4
     d2h = 8
 
+    copy_stream = torch.cuda.Stream(device=dev)
+
     def e2e_step(step):
         v = view_of(step)
+        main = torch.cuda.current_stream(dev)
+        # the camera is needed first (small, on the compute stream); the 25 MB dL/dimg upload runs on a
+        # copy stream underneath the forward render and is joined just before the backward needs it
         E = host["extrinsic_matrix"][v].to(dev, non_blocking=True)
         I = host["intrinsic_params"].to(dev, non_blocking=True)
         Cc = host["camera_center"][v].to(dev, non_blocking=True)
-        G = host_dimg.to(dev, non_blocking=True)
+        copy_stream.wait_stream(main)
+        with torch.cuda.stream(copy_stream):
+            G = host_dimg.to(dev, non_blocking=True)
         for p_ in params.values():
             p_.grad = None
         out = r.render_iter(H, W, E, I, Cc, **params)
         img = out["rendered_features_split"]["rgb"]
+        main.wait_stream(copy_stream)
+        G.record_stream(main)
         loss = (img * G).sum()
         loss.backward()
         if world > 1:
@@ -266,7 +275,7 @@ def main():
             parallel.allreduce_step([p_.grad for p_ in params.values()], out["uv_points"].grad, out["radii"], world)
         res = torch.stack([loss.detach(), out["visibility"].sum().float()])
         res_host.copy_(res, non_blocking=True)
-        torch.cuda.current_stream().synchronize()  # the caller consumes the result every step
+        main.synchronize()  # the caller consumes the result every step
         return float(res_host[0])
 
     for s in range(3):

@@ -80,7 +80,7 @@ def ensure_init() -> None:
 KERNELS_PER_CALL = {
     "pxb_project_point_forward": 1, "pxb_project_point_backward": 1, "pxb_compute_cov3d_forward": 1,
     "pxb_compute_cov3d_backward": 1, "pxb_ewa_project_forward": 1, "pxb_ewa_project_backward": 1,
-    "pxb_compute_sh_forward": 1, "pxb_compute_sh_backward": 1, "pxb_bin_prepare": 8, "pxb_sort_gaussian": 4,
+    "pxb_compute_sh_forward": 1, "pxb_compute_sh_backward": 1, "pxb_bin_prepare": 14, "pxb_sort_gaussian": 8,
     "pxb_pack_records": 1, "pxb_unpack_grads": 1, "pxb_blend_forward": 1, "pxb_blend_backward": 1,
     "pxb_fused_forward": 1, "pxb_fused_backward": 1,
 }
@@ -120,7 +120,7 @@ def launch(name: str, *args) -> None:
     if name == "pxb_sort_gaussian":
         W, H = args[8], args[9]
         nt = ((W + 15) // 16) * ((H + 15) // 16)
-        n = (4 + max(1, (max(nt - 1, 0).bit_length() + 7) // 8)) if args[1] > 0 else 0
+        n = (2 + 3 * max(1, (max(nt - 1, 0).bit_length() + 7) // 8)) if args[1] > 0 else 0
     launch_count += n
     if _timer is None:
         check(fn(*args), name)

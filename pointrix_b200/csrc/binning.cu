@@ -11,8 +11,8 @@
 //   4. stable radix sort of the N pairs by TILE ID ONLY (ceil(log2 tiles)/8 = 2 passes at 1080p):
 //      stability carries the (depth, id) order of step 1 into every tile;
 //   5. per-tile [first,last) ranges from the sorted tile ids.
-// All radix passes are onesweep style (one histogram pass, then one read + one write of the pairs
-// per 8-bit digit with decoupled look-back).  Integer work throughout: idx_sorted and tile_range
+// Radix passes are chain-free (per-tile digit histogram, scan over tiles, scatter; digits of <= 8 bits,
+// the significant bits split evenly over the passes).  Integer work throughout: idx_sorted and tile_range
 // are bit-identical to the reference's; the 64-bit sorted keys can be rebuilt for inspection.
 #include "common.cuh"
 #include "pointrix_b200.h"
@@ -174,89 +174,139 @@ emit_keys_kernel(int P, const float* __restrict__ uv, int uv_stride, const int* 
 }
 
 // ---------------------------------------------------------------------------
-// onesweep LSD radix sort, 8-bit digits, 32-bit keys + 32-bit values
+// LSD radix sort, digits of <= 8 bits, 32-bit keys + 32-bit values.
+// Each pass is three chain-free kernels:
+//   rs_tile_hist  : digit histogram of every 4096-pair tile            -> counts[digit][tile]
+//   rs_tile_scan  : exclusive scan over tiles, per digit (+ digit totals)
+//   rs_scatter    : stable in-CTA ranking, shared-memory exchange, coalesced write-out at
+//                   base(digit) + counts_excl[digit][tile]
+// A single-pass ("onesweep") variant with decoupled look-back was measured first: with ~600 resident
+// CTAs every wave restarts the look-back chain (tile t needs the aggregates of all unfinished
+// predecessors), which cost 30+ us per wave -- 5x the data movement time.  Re-reading the keys once
+// per pass (4 B/pair) removes every inter-CTA dependency.
 // ---------------------------------------------------------------------------
 constexpr int kRsThreads = 256;
 constexpr int kRsItems = 16;
 constexpr int kRsTile = kRsThreads * kRsItems;  // 4096 pairs per CTA
 constexpr int kRadix = 256;
 constexpr int kMaxPasses = 4;
-#define kStAgg (1u << 30)
-#define kStPrefix (2u << 30)
-#define kStMask ((1u << 30) - 1u)
 
-__global__ void __launch_bounds__(kRsThreads)
-rs_histogram_kernel(const unsigned int* __restrict__ keys, int N_cap, const int* __restrict__ n_dev, int passes,
-                    unsigned int* __restrict__ hist) {
-    __shared__ unsigned int h[kMaxPasses][kRadix];
-    const int N = n_dev ? min(*n_dev, N_cap) : N_cap;
-    for (int k = threadIdx.x; k < kMaxPasses * kRadix; k += blockDim.x) (&h[0][0])[k] = 0;
-    __syncthreads();
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (long long)gridDim.x * blockDim.x) {
-        const unsigned int k = keys[i];
-        for (int p = 0; p < passes; p++) atomicAdd(&h[p][(k >> (8 * p)) & 255u], 1u);
+// digit layout of one radix sort: pass p ranks bits [shift[p], shift[p]+bits[p]) (bits <= 8)
+struct RsDigits {
+    int passes;
+    int shift[kMaxPasses];
+    int bits[kMaxPasses];
+};
+// `total_bits` significant key bits split into ceil(total/8) passes of near-equal width
+static RsDigits make_digits(int total_bits) {
+    RsDigits d;
+    d.passes = max(1, (total_bits + 7) / 8);
+    int done = 0;
+    for (int p = 0; p < kMaxPasses; p++) {
+        const int left = d.passes - p;
+        const int b = p < d.passes ? (total_bits - done + left - 1) / left : 0;
+        d.shift[p] = done;
+        d.bits[p] = max(b, p < d.passes ? 1 : 0);
+        done += b;
     }
+    return d;
+}
+
+template <int NBITS>
+__global__ void __launch_bounds__(kRsThreads)
+rs_tile_hist_kernel(const unsigned int* __restrict__ keys, int N_cap, const int* __restrict__ n_dev, int shift, int T,
+                    unsigned int* __restrict__ counts /*[2^NBITS][T]*/) {
+    constexpr int NB = 1 << NBITS;
+    constexpr int NW = kRsThreads / 32;
+    __shared__ unsigned int h[NW][NB];  // warp-private: 8x less contention on skewed digits
+    const int N = n_dev ? min(*n_dev, N_cap) : N_cap;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    for (int k = tid; k < NW * NB; k += kRsThreads) (&h[0][0])[k] = 0;
     __syncthreads();
-    for (int k = threadIdx.x; k < passes * kRadix; k += blockDim.x) {
-        const unsigned int c = (&h[0][0])[k];
-        if (c) atomicAdd(hist + k, c);
+    const long long base = (long long)blockIdx.x * kRsTile;
+    unsigned int key[kRsItems];
+#pragma unroll
+    for (int k = 0; k < kRsItems; k++) {
+        const long long p = base + k * kRsThreads + tid;
+        key[k] = p < N ? keys[p] : 0u;
+    }
+#pragma unroll
+    for (int k = 0; k < kRsItems; k++)
+        if (base + k * kRsThreads + tid < N) atomicAdd(&h[warp][(key[k] >> shift) & (NB - 1)], 1u);
+    __syncthreads();
+    for (int k = tid; k < NB; k += kRsThreads) {
+        unsigned int c = 0;
+#pragma unroll
+        for (int w = 0; w < NW; w++) c += h[w][k];
+        counts[(size_t)k * T + blockIdx.x] = c;
     }
 }
 
-// exclusive scan over the 256 bins of every pass (one block per pass)
-__global__ void rs_scan_hist_kernel(unsigned int* __restrict__ hist) {
-    __shared__ unsigned int s_warp[kRadix / 32];
-    unsigned int* h = hist + blockIdx.x * kRadix;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const unsigned int c = h[threadIdx.x];
-    unsigned int incl = c;
+// one CTA per digit: exclusive scan of counts[digit][0..T) in place, totals[digit] = row sum
+__global__ void __launch_bounds__(1024) rs_tile_scan_kernel(unsigned int* __restrict__ counts, int T,
+                                                            unsigned int* __restrict__ totals) {
+    __shared__ unsigned int s_warp[32];
+    __shared__ unsigned int s_total;
+    unsigned int* row = counts + (size_t)blockIdx.x * T;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    unsigned int carry = 0;
+    for (int base = 0; base < T; base += 1024) {
+        const int i = base + tid;
+        const unsigned int c = i < T ? row[i] : 0u;
+        unsigned int incl = c;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const unsigned int n = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += n;
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned int n = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += n;
+        }
+        if (lane == 31) s_warp[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            const unsigned int w = s_warp[lane];
+            unsigned int wi = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned int n = __shfl_up_sync(0xffffffffu, wi, o);
+                if (lane >= o) wi += n;
+            }
+            s_warp[lane] = wi - w;  // exclusive warp offsets
+            if (lane == 31) s_total = wi;
+        }
+        __syncthreads();
+        if (i < T) row[i] = carry + s_warp[warp] + incl - c;
+        carry += s_total;
+        __syncthreads();
     }
-    if (lane == 31) s_warp[warp] = incl;
-    __syncthreads();
-    unsigned int off = 0;
-    for (int w = 0; w < warp; w++) off += s_warp[w];
-    h[threadIdx.x] = off + incl - c;
+    if (tid == 0) totals[blockIdx.x] = carry;
 }
 
 struct RsSmem {
-    unsigned int keys[kRsTile];
-    unsigned int vals[kRsTile];
+    uint2 pairs[kRsTile];  // (key, value) exchange buffer; its first 16 KB double as the match masks
     unsigned int warp_hist[kRsThreads / 32][kRadix];
     unsigned int digit_start[kRadix];
-    long long gbase[kRadix];
+    int gbase[kRadix];
     unsigned int warp_sums[kRadix / 32];
-    int tile;
 };
 
-__global__ void __launch_bounds__(kRsThreads)
-rs_onesweep_kernel(const unsigned int* __restrict__ keys_in, const unsigned int* __restrict__ vals_in,
-                   unsigned int* __restrict__ keys_out, unsigned int* __restrict__ vals_out, int N_cap,
-                   const int* __restrict__ n_dev, int shift, const unsigned int* __restrict__ bin_base /*[256] exclusive*/,
-                   unsigned int* status, unsigned int* ticket) {
-    const int N = n_dev ? min(*n_dev, N_cap) : N_cap;
-    __shared__ RsSmem sm;
+// FULL: the tile holds exactly kRsTile pairs (every tile but the last) -- no bounds predicates
+template <int NBITS, bool FULL>
+__device__ __forceinline__ void rs_scatter_tile(RsSmem& sm, const unsigned int* __restrict__ keys_in,
+                                                const unsigned int* __restrict__ vals_in,
+                                                unsigned int* __restrict__ keys_out, unsigned int* __restrict__ vals_out,
+                                                long long tile_base, int tile_n, int shift, int T, int tile,
+                                                const unsigned int* __restrict__ counts_excl,
+                                                const unsigned int* __restrict__ totals) {
+    constexpr int NB = 1 << NBITS;
+    constexpr unsigned int kDigitMask = NB - 1u;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) sm.tile = (int)atomicAdd(ticket, 1u);
-    for (int k = tid; k < (kRsThreads / 32) * kRadix; k += kRsThreads) (&sm.warp_hist[0][0])[k] = 0;
-    __syncthreads();
-    const int tile = sm.tile;
-    if ((long long)tile * kRsTile >= N) return;  // capacity-sized grid: surplus CTAs leave
-    const long long tile_base = (long long)tile * kRsTile;
-    const int tile_n = (int)min((long long)kRsTile, (long long)N - tile_base);
-
     // warp-striped load: item k of lane l in warp w sits at w*32*IPT + k*32 + l
     unsigned int key[kRsItems];
     unsigned int val[kRsItems];
-    unsigned int rank[kRsItems];
     const int wbase = warp * 32 * kRsItems + lane;
 #pragma unroll
     for (int k = 0; k < kRsItems; k++) {
         const int p = wbase + k * 32;
-        if (p < tile_n) {
+        if (FULL || p < tile_n) {
             key[k] = keys_in[tile_base + p];
             val[k] = vals_in[tile_base + p];
         } else {
@@ -264,96 +314,73 @@ rs_onesweep_kernel(const unsigned int* __restrict__ keys_in, const unsigned int*
             val[k] = 0;
         }
     }
-    // warp-level stable ranking; counters private to the warp.  The peer masks of all items are
-    // computed first (independent, they pipeline); only the short leader read-modify-write of the
-    // warp-private counter is serial per item.
+    // this tile's global write bases (independent of the ranking below: issue the loads early)
+    const unsigned int my_total = tid < NB ? totals[tid] : 0u;
+    const unsigned int my_excl = tid < NB ? counts_excl[(size_t)tid * T + tile] : 0u;
+
+    // Warp-level stable ranking; counters private to the warp.  The lanes holding the same digit
+    // ("peers") are found by OR-ing lane bits into a warp-private shared-memory word per digit
+    // (measured on B200 for 11 M keys: +8 us, against +22 us for NBITS ballots and +64 us for
+    // MATCH.ANY); two mask buffers alternate so that clearing overlaps the next item.  Every lane
+    // reads the digit's running count, the first peer adds the group size: no shuffle, no branch.
     const unsigned int lt_mask = (1u << lane) - 1u;
     unsigned int* wh = sm.warp_hist[warp];
-    unsigned int peers[kRsItems];
+    unsigned int* mk = reinterpret_cast<unsigned int*>(sm.pairs) + warp * (2 * kRadix);
+    for (int k = lane; k < 2 * NB; k += 32) mk[(k / NB) * kRadix + (k % NB)] = 0;
+    __syncwarp();
+    unsigned int rank2[kRsItems / 2];  // two 16-bit ranks per register (rank < kRsTile = 4096)
 #pragma unroll
     for (int k = 0; k < kRsItems; k++) {
-        const bool valid = (wbase + k * 32) < tile_n;
-        const unsigned int d = (key[k] >> shift) & 255u;
-        const unsigned int vmask = __ballot_sync(0xffffffffu, valid);
-        const unsigned int m = __match_any_sync(0xffffffffu, d);  // all lanes participate
-        peers[k] = valid ? (m & vmask) : 0u;
-    }
-#pragma unroll
-    for (int k = 0; k < kRsItems; k++) {
-        const unsigned int d = (key[k] >> shift) & 255u;
-        unsigned int old = 0;
-        const int leader = peers[k] ? (__ffs(peers[k]) - 1) : 0;
-        if (peers[k] && lane == leader) {
-            old = wh[d];
-            wh[d] = old + __popc(peers[k]);
-        }
-        old = __shfl_sync(0xffffffffu, old, leader);
-        rank[k] = old + __popc(peers[k] & lt_mask);
+        const bool valid = FULL || (wbase + k * 32) < tile_n;
+        const unsigned int d = (key[k] >> shift) & kDigitMask;
+        unsigned int* m = mk + (k & 1) * kRadix;
+        if (valid) atomicOr(&m[d], 1u << lane);
         __syncwarp();
+        const unsigned int peers = m[d];
+        const unsigned int old = wh[d];
+        // the other buffer was last read one item ago: clear it before the next item ORs into it
+        if (k > 0) mk[((k - 1) & 1) * kRadix + ((key[k - 1] >> shift) & kDigitMask)] = 0;
+        const unsigned int below = __popc(peers & lt_mask);
+        const unsigned int r = old + below;
+        if (k & 1) rank2[k >> 1] |= r << 16; else rank2[k >> 1] = r;
+        __syncwarp();
+        if (valid && below == 0) wh[d] = old + __popc(peers);
     }
     __syncthreads();
-    // per-digit: exclusive offsets across warps, tile total, publish for look-back
-    unsigned int count = 0;
+    // per digit (thread = digit): exclusive offsets across warps, start of the digit inside the
+    // sorted tile, start of the digit in the output (exclusive scan of the totals)
     {
+        unsigned int count = 0;
 #pragma unroll
         for (int w = 0; w < kRsThreads / 32; w++) {
             const unsigned int c = sm.warp_hist[w][tid];
             sm.warp_hist[w][tid] = count;
             count += c;
         }
-        volatile unsigned int* st = status + (size_t)tile * kRadix + tid;
-        *st = (tile == 0 ? kStPrefix : kStAgg) | count;
-    }
-    // exclusive scan of tile totals over digits -> start of each digit inside the sorted tile
-    {
-        unsigned int incl = count;
+        unsigned int incl = count, tincl = my_total;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             const unsigned int n = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += n;
+            const unsigned int tn = __shfl_up_sync(0xffffffffu, tincl, o);
+            if (lane >= o) { incl += n; tincl += tn; }
         }
-        if (lane == 31) sm.warp_sums[warp] = incl;
+        if (lane == 31) { sm.warp_sums[warp] = incl; sm.digit_start[warp] = tincl; }  // digit_start reused as scratch
         __syncthreads();
-        unsigned int off = 0;
-        for (int w = 0; w < warp; w++) off += sm.warp_sums[w];
-        sm.digit_start[tid] = off + incl - count;
-    }
-    // decoupled look-back: digits are independent, one thread per digit.  Eight predecessors are
-    // probed per round trip (independent loads) so that the first wave, where every resident CTA
-    // still holds only its aggregate, is walked 8 tiles per L2 latency instead of one.
-    {
-        unsigned int excl = 0;
-        if (tile > 0) {
-            const volatile unsigned int* st = status + tid;
-            int t = tile - 1;
-            bool done_lb = false;
-            while (!done_lb) {
-                unsigned int sv[8];
-#pragma unroll
-                for (int u = 0; u < 8; u++) sv[u] = (t - u >= 0) ? st[(size_t)(t - u) * kRadix] : kStPrefix;
-#pragma unroll
-                for (int u = 0; u < 8; u++) {
-                    if (done_lb) break;
-                    const unsigned int flag = sv[u] >> 30;
-                    if (flag == 0) break;  // not published yet: re-probe from this tile
-                    excl += sv[u] & kStMask;
-                    t--;
-                    if (flag == 2) done_lb = true;
-                }
-            }
-            *((volatile unsigned int*)(status + (size_t)tile * kRadix + tid)) = kStPrefix | (excl + count);
-        }
-        sm.gbase[tid] = (long long)bin_base[tid] + (long long)excl - (long long)sm.digit_start[tid];
+        unsigned int off = 0, toff = 0;
+        for (int w = 0; w < warp; w++) { off += sm.warp_sums[w]; toff += sm.digit_start[w]; }
+        __syncthreads();
+        const unsigned int dstart = off + incl - count;
+        sm.digit_start[tid] = dstart;
+        sm.gbase[tid] = (int)(toff + tincl - my_total + my_excl) - (int)dstart;
     }
     __syncthreads();
     // scatter into tile-local sorted order
 #pragma unroll
     for (int k = 0; k < kRsItems; k++) {
-        if ((wbase + k * 32) < tile_n) {
-            const unsigned int d = (key[k] >> shift) & 255u;
-            const unsigned int pos = sm.digit_start[d] + sm.warp_hist[warp][d] + rank[k];
-            sm.keys[pos] = key[k];
-            sm.vals[pos] = val[k];
+        if (FULL || (wbase + k * 32) < tile_n) {
+            const unsigned int d = (key[k] >> shift) & kDigitMask;
+            const unsigned int pos = sm.digit_start[d] + sm.warp_hist[warp][d] + ((rank2[k >> 1] >> (16 * (k & 1))) & 0xffffu);
+            sm.pairs[pos] = make_uint2(key[k], val[k]);
         }
     }
     __syncthreads();
@@ -361,35 +388,67 @@ rs_onesweep_kernel(const unsigned int* __restrict__ keys_in, const unsigned int*
 #pragma unroll
     for (int k = 0; k < kRsItems; k++) {
         const int p = k * kRsThreads + tid;
-        if (p < tile_n) {
-            const unsigned int kk = sm.keys[p];
-            const unsigned int d = (kk >> shift) & 255u;
-            const long long dst = sm.gbase[d] + p;
-            keys_out[dst] = kk;
-            vals_out[dst] = sm.vals[p];
+        if (FULL || p < tile_n) {
+            const uint2 kv = sm.pairs[p];
+            const int dst = sm.gbase[(kv.x >> shift) & kDigitMask] + p;
+            keys_out[dst] = kv.x;
+            vals_out[dst] = kv.y;
         }
     }
+}
+
+template <int NBITS>
+__global__ void __launch_bounds__(kRsThreads, 3)
+rs_scatter_kernel(const unsigned int* __restrict__ keys_in, const unsigned int* __restrict__ vals_in,
+                  unsigned int* __restrict__ keys_out, unsigned int* __restrict__ vals_out, int N_cap,
+                  const int* __restrict__ n_dev, int shift, int T, const unsigned int* __restrict__ counts_excl,
+                  const unsigned int* __restrict__ totals) {
+    const int N = n_dev ? min(*n_dev, N_cap) : N_cap;
+    __shared__ RsSmem sm;
+    const int tile = blockIdx.x;
+    const long long tile_base = (long long)tile * kRsTile;
+    if (tile_base >= N) return;  // capacity-sized grid: surplus CTAs leave
+    for (int k = threadIdx.x; k < (kRsThreads / 32) * kRadix; k += kRsThreads) (&sm.warp_hist[0][0])[k] = 0;
+    __syncthreads();
+    const int tile_n = (int)min((long long)kRsTile, (long long)N - tile_base);
+    if (tile_n == kRsTile)
+        rs_scatter_tile<NBITS, true>(sm, keys_in, vals_in, keys_out, vals_out, tile_base, tile_n, shift, T, tile, counts_excl, totals);
+    else
+        rs_scatter_tile<NBITS, false>(sm, keys_in, vals_in, keys_out, vals_out, tile_base, tile_n, shift, T, tile, counts_excl, totals);
 }
 
 // ---------------------------------------------------------------------------
 // tile ranges (sort_gaussian.cu:45-71) from the sorted tile ids
 // ---------------------------------------------------------------------------
-__global__ void tile_range_kernel(int N_cap, const int* __restrict__ n_dev, const unsigned int* __restrict__ tile_sorted,
-                                  int num_tiles, int2* __restrict__ tile_range) {
+__global__ void __launch_bounds__(256)
+tile_range_kernel(int N_cap, const int* __restrict__ n_dev, const unsigned int* __restrict__ tile_sorted,
+                  int num_tiles, int2* __restrict__ tile_range) {
     const int N = n_dev ? min(*n_dev, N_cap) : N_cap;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= N) return;
-    const unsigned int cur = tile_sorted[i];
-    if (cur >= (unsigned)num_tiles) return;
-    if (i == 0) tile_range[cur].x = 0;
-    else {
-        const unsigned int prev = tile_sorted[i - 1];
-        if (prev != cur) {
+    // four consecutive entries per thread (one 16-byte load) plus the entry before them
+    const int i0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (i0 >= N) return;
+    unsigned int v[5];
+    v[0] = i0 > 0 ? tile_sorted[i0 - 1] : 0xffffffffu;
+    if (i0 + 4 <= N) {
+        const uint4 q = *reinterpret_cast<const uint4*>(tile_sorted + i0);
+        v[1] = q.x; v[2] = q.y; v[3] = q.z; v[4] = q.w;
+    } else {
+#pragma unroll
+        for (int k = 0; k < 4; k++) v[1 + k] = (i0 + k < N) ? tile_sorted[i0 + k] : 0xffffffffu;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const int i = i0 + k;
+        if (i >= N) break;
+        const unsigned int cur = v[1 + k], prev = v[k];
+        if (cur >= (unsigned)num_tiles) continue;
+        if (i == 0) tile_range[cur].x = 0;
+        else if (prev != cur) {
             tile_range[cur].x = i;
             if (prev < (unsigned)num_tiles) tile_range[prev].y = i;
         }
+        if (i == N - 1) tile_range[cur].y = N;
     }
-    if (i == N - 1) tile_range[cur].y = N;
 }
 
 // the reference's sorted int64 keys, rebuilt for inspection / tests
@@ -406,13 +465,14 @@ static inline int ceil_log2(int x) {
     while ((1ll << b) < x) b++;
     return b;
 }
-static inline int tile_passes(int num_tiles) { return max(1, (ceil_log2(num_tiles) + 7) / 8); }
+static inline int tile_bits(int num_tiles) { return max(1, ceil_log2(num_tiles)); }
+static inline int tile_passes(int num_tiles) { return (tile_bits(num_tiles) + 7) / 8; }
 
 // P-sized workspace: survives from pxb_bin_prepare to pxb_sort_gaussian
 struct WsP {
     unsigned char* ctl; size_t ctl_bytes;          // zeroed per call
     unsigned long long* scan_status; unsigned int* scan_ticket;
-    unsigned int* hist; unsigned int* rs_ticket; unsigned int* rs_status;
+    unsigned int* totals; unsigned int* counts;
     unsigned int* keys[2]; unsigned int* vals[2];  // depth-sort ping-pong; result in keys[0]/vals[0] (4 passes)
     int* offsets;
     size_t total;
@@ -426,10 +486,9 @@ static WsP carve_p(void* ws, int P) {
     b.ctl = base;
     b.scan_status = (unsigned long long*)(base + o); o += align_up(scan_tiles * 8, 256);
     b.scan_ticket = (unsigned int*)(base + o); o += 256;
-    b.hist = (unsigned int*)(base + o); o += align_up((size_t)4 * kRadix * 4, 256);
-    b.rs_ticket = (unsigned int*)(base + o); o += 256;
-    b.rs_status = (unsigned int*)(base + o); o += align_up((size_t)4 * rs_tiles * kRadix * 4, 256);
     b.ctl_bytes = o;
+    b.totals = (unsigned int*)(base + o); o += align_up((size_t)kRadix * 4, 256);
+    b.counts = (unsigned int*)(base + o); o += align_up(rs_tiles * kRadix * 4, 256);
     for (int k = 0; k < 2; k++) {
         b.keys[k] = (unsigned int*)(base + o); o += align_up((size_t)P * 4, 256);
         b.vals[k] = (unsigned int*)(base + o); o += align_up((size_t)P * 4, 256);
@@ -441,7 +500,7 @@ static WsP carve_p(void* ws, int P) {
 // N-sized workspace of pxb_sort_gaussian
 struct WsN {
     unsigned char* ctl; size_t ctl_bytes;
-    unsigned int* hist; unsigned int* rs_ticket; unsigned int* rs_status;
+    unsigned int* totals; unsigned int* counts;
     unsigned int* keys[2]; unsigned int* vals_tmp;
     size_t total;
 };
@@ -452,27 +511,42 @@ static WsN carve_n(void* ws, long long Ncap, int num_tiles) {
     size_t o = 0;
     unsigned char* base = (unsigned char*)ws;
     b.ctl = base;
-    b.hist = (unsigned int*)(base + o); o += align_up((size_t)kMaxPasses * kRadix * 4, 256);
-    b.rs_ticket = (unsigned int*)(base + o); o += 256;
-    b.rs_status = (unsigned int*)(base + o); o += align_up((size_t)passes * rs_tiles * kRadix * 4, 256);
-    b.ctl_bytes = o;
+    b.ctl_bytes = 0;
+    b.totals = (unsigned int*)(base + o); o += align_up((size_t)kRadix * 4, 256);
+    b.counts = (unsigned int*)(base + o); o += align_up(rs_tiles * kRadix * 4, 256);
     for (int k = 0; k < 2; k++) { b.keys[k] = (unsigned int*)(base + o); o += align_up((size_t)Ncap * 4, 256); }
     b.vals_tmp = (unsigned int*)(base + o); o += align_up((size_t)Ncap * 4, 256);
     b.total = o;
     return b;
 }
 
-// one stable LSD radix sort over `passes` 8-bit digits starting at bit 0; result lands in (k[passes&1], v[passes&1])
-static int radix_sort_u32(unsigned int* k[2], unsigned int* v[2], int N_cap, const int* n_dev, int passes,
-                          unsigned int* hist, unsigned int* status, unsigned int* ticket, cudaStream_t s) {
-    const int rs_tiles = (N_cap + kRsTile - 1) / kRsTile;
-    const int hist_blocks = (int)min((long long)(148 * 8), ((long long)N_cap + kRsThreads * 8 - 1) / (kRsThreads * 8));
-    rs_histogram_kernel<<<hist_blocks, kRsThreads, 0, s>>>(k[0], N_cap, n_dev, passes, hist);
-    rs_scan_hist_kernel<<<passes, kRadix, 0, s>>>(hist);
-    for (int p = 0; p < passes; p++) {
-        rs_onesweep_kernel<<<rs_tiles, kRsThreads, 0, s>>>(k[p & 1], v[p & 1], k[(p + 1) & 1], v[(p + 1) & 1], N_cap, n_dev,
-                                                          8 * p, hist + p * kRadix,
-                                                          status + (size_t)p * (rs_tiles + 1) * kRadix, ticket + p);
+template <int NBITS>
+static void launch_pass(int T, const unsigned int* ki, const unsigned int* vi, unsigned int* ko, unsigned int* vo, int N_cap,
+                        const int* n_dev, int shift, unsigned int* counts, unsigned int* totals, cudaStream_t s) {
+    static bool attr = false;
+    if (!attr) {  // shared memory, not L1, is what the scatter kernel lives on
+        cudaFuncSetAttribute(rs_scatter_kernel<NBITS>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        attr = true;
+    }
+    rs_tile_hist_kernel<NBITS><<<T, kRsThreads, 0, s>>>(ki, N_cap, n_dev, shift, T, counts);
+    rs_tile_scan_kernel<<<1 << NBITS, 1024, 0, s>>>(counts, T, totals);
+    rs_scatter_kernel<NBITS><<<T, kRsThreads, 0, s>>>(ki, vi, ko, vo, N_cap, n_dev, shift, T, counts, totals);
+}
+
+// one stable LSD radix sort over the low `total_bits` key bits; result lands in (k[passes&1], v[passes&1]).
+// counts: kRadix * T words of scratch, totals: kRadix words (neither needs initialising)
+static int radix_sort_u32(unsigned int* k[2], unsigned int* v[2], int N_cap, const int* n_dev, int total_bits,
+                          unsigned int* counts, unsigned int* totals, cudaStream_t s) {
+    const RsDigits dg = make_digits(total_bits);
+    const int T = (N_cap + kRsTile - 1) / kRsTile;
+    for (int p = 0; p < dg.passes; p++) {
+        const unsigned int *ki = k[p & 1], *vi = v[p & 1];
+        unsigned int *ko = k[(p + 1) & 1], *vo = v[(p + 1) & 1];
+        switch (dg.bits[p]) {
+#define PXB_PASS(B) case B: launch_pass<B>(T, ki, vi, ko, vo, N_cap, n_dev, dg.shift[p], counts, totals, s); break;
+            PXB_PASS(1) PXB_PASS(2) PXB_PASS(3) PXB_PASS(4) PXB_PASS(5) PXB_PASS(6) PXB_PASS(7) PXB_PASS(8)
+#undef PXB_PASS
+        }
     }
     return (int)cudaGetLastError();
 }
@@ -500,7 +574,7 @@ int pxb_bin_prepare(int P, const float* depth, const int* radius, const int* til
     if (ws_p_bytes < b.total) return PXB_ERR_WORKSPACE;
     PXB_CUDA_OK(cudaMemsetAsync(b.ctl, 0, b.ctl_bytes, s));
     init_depth_keys_kernel<<<(P + 255) / 256, 256, 0, s>>>(P, depth, b.keys[0], b.vals[0]);
-    int rc = radix_sort_u32(b.keys, b.vals, P, nullptr, 4, b.hist, b.rs_status, b.rs_ticket, s);  // -> keys[0]/vals[0]
+    int rc = radix_sort_u32(b.keys, b.vals, P, nullptr, 32, b.counts, b.totals, s);  // -> keys[0]/vals[0]
     if (rc) return rc;
     scan_kernel<<<(P + kScanTile - 1) / kScanTile, kScanThreads, 0, s>>>(P, tiles, radius, b.vals[0], b.offsets, total_dev,
                                                                         b.scan_status, b.scan_ticket);
@@ -523,7 +597,6 @@ int pxb_sort_gaussian(int P, long long N, const int* total_dev, const float* uv,
     WsN bn = carve_n(ws_n, N, num_tiles);
     if (ws_p_bytes < bp.total || ws_n_bytes < bn.total) return PXB_ERR_WORKSPACE;
     const int passes = tile_passes(num_tiles);
-    PXB_CUDA_OK(cudaMemsetAsync(bn.ctl, 0, bn.ctl_bytes, s));
     // ping-pong so that the last pass writes the values straight into idx_sorted
     unsigned int* k[2] = {bn.keys[0], bn.keys[1]};
     unsigned int* v[2];
@@ -531,10 +604,10 @@ int pxb_sort_gaussian(int P, long long N, const int* total_dev, const float* uv,
     v[(passes + 1) & 1] = bn.vals_tmp;
     emit_keys_kernel<<<(P + kEmitThreads - 1) / kEmitThreads, kEmitThreads, 0, s>>>(
         P, uv, uv_stride, radius, tiles, bp.vals[0], bp.offsets, gx, gy, N, total_dev, k[0], v[0]);
-    int rc = radix_sort_u32(k, v, (int)N, total_dev, passes, bn.hist, bn.rs_status, bn.rs_ticket, s);
+    int rc = radix_sort_u32(k, v, (int)N, total_dev, tile_bits(num_tiles), bn.counts, bn.totals, s);
     if (rc) return rc;
     const unsigned int* tile_sorted = k[passes & 1];
-    tile_range_kernel<<<(int)((N + 255) / 256), 256, 0, s>>>((int)N, total_dev, tile_sorted, num_tiles, (int2*)tile_range);
+    tile_range_kernel<<<(int)((N + 1023) / 1024), 256, 0, s>>>((int)N, total_dev, tile_sorted, num_tiles, (int2*)tile_range);
     if (keys_sorted_out && total_dev == nullptr)
         rebuild_keys_kernel<<<(int)((N + 255) / 256), 256, 0, s>>>((int)N, tile_sorted, idx_sorted, depth, keys_sorted_out);
     return (int)cudaGetLastError();

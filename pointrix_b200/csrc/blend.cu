@@ -188,7 +188,7 @@ constexpr int kSlots = 16;
 constexpr int kSlotPitch = 33;  // float2 units: conflict-free row (phase 1) and column (phase 2) access
 
 template <int CH, int S>
-__global__ void __launch_bounds__(kBlendThreads)
+__global__ void __launch_bounds__(kBlendThreads, (CH <= 4 ? 4 : 1))
 blend_bwd_kernel(const float* __restrict__ rec, const int* __restrict__ idx_sorted, const int2* __restrict__ tile_range,
                  float bg, int C, int W, int H, int gx, const float* __restrict__ final_T,
                  const int* __restrict__ ncontrib, const float* __restrict__ dL_dout, float* __restrict__ grec) {
@@ -423,8 +423,11 @@ static int launch_fwd(const float* rec, const int* idx_sorted, const int* tile_r
     const int gx = (W + PXB_TILE - 1) / PXB_TILE, gy = (H + PXB_TILE - 1) / PXB_TILE;
     const size_t smem = (size_t)kBatch * S * 4 + kBatch * 4 + kBatch;
     static bool attr = false;
-    if (!attr && smem > 48 * 1024) {
-        PXB_CUDA_OK(cudaFuncSetAttribute(blend_fwd_kernel<CH, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (!attr) {
+        if (smem > 48 * 1024)
+            PXB_CUDA_OK(cudaFuncSetAttribute(blend_fwd_kernel<CH, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        PXB_CUDA_OK(cudaFuncSetAttribute(blend_fwd_kernel<CH, S>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                         cudaSharedmemCarveoutMaxShared));
         attr = true;
     }
     blend_fwd_kernel<CH, S><<<dim3(gx, gy), kBlendThreads, smem, s>>>(rec, idx_sorted, (const int2*)tile_range, bg, C, W,
@@ -439,8 +442,11 @@ static int launch_bwd(const float* rec, const int* idx_sorted, const int* tile_r
     constexpr int CHP = (CH + 3) & ~3, NW = kBlendThreads / 32;
     const size_t smem = (size_t)(kBatch * S + NW * 32 * CHP + 2 * NW * kSlots * kSlotPitch) * 4 + kBatch * 4 + kBatch;
     static bool attr = false;
-    if (!attr && smem > 48 * 1024) {
-        PXB_CUDA_OK(cudaFuncSetAttribute(blend_bwd_kernel<CH, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (!attr) {
+        if (smem > 48 * 1024)
+            PXB_CUDA_OK(cudaFuncSetAttribute(blend_bwd_kernel<CH, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        PXB_CUDA_OK(cudaFuncSetAttribute(blend_bwd_kernel<CH, S>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                         cudaSharedmemCarveoutMaxShared));
         attr = true;
     }
     blend_bwd_kernel<CH, S><<<dim3(gx, gy), kBlendThreads, smem, s>>>(
