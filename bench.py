@@ -113,7 +113,7 @@ def cpu_oracle_run(cfg_name: str, sample_P: int, steps: int, warmup: int):
             "s_per_view_sample": t_sample}
 
 
-def run_reference(args):
+def run_reference(args, out_f):
     rank = env_int("RANK", 0)
     if rank != 0:
         return
@@ -124,7 +124,7 @@ def run_reference(args):
             "config": {"workload": workload_name(args.config), "parallelism": "cpu"},
             "cpu_baseline": r, "gpu_launches": 0,
             "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    print(json.dumps(line), file=out_f)
 
 
 def workload_name(cfg):
@@ -135,7 +135,24 @@ def workload_name(cfg):
             f"MsplatRender.render_iter fwd + bwd of <G,img> (one view per GPU per step)")
 
 
+def _claim_stdout():
+    """The contract is ONE JSON line on stdout: libraries that print there (NCCL's version banner)
+    are sent to stderr; the returned file object is the real stdout."""
+    real = os.fdopen(os.dup(1), "w")
+    sys.stdout.flush()
+    os.dup2(2, 1)
+    return real
+
+
 def main():
+    out_f = _claim_stdout()
+    try:
+        _main(out_f)
+    finally:
+        out_f.flush()
+
+
+def _main(out_f):
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -147,13 +164,13 @@ def main():
     ap.add_argument("--no-ref-gpu", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
-        return run_reference(args)
+        return run_reference(args, out_f)
 
     import torch
     import torch.distributed as dist
 
     import pointrix_b200 as pb
-    from pointrix_b200 import _lib, scene
+    from pointrix_b200 import _lib, parallel, scene
 
     rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
     assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback)"
@@ -167,7 +184,9 @@ def main():
     H, W, P, V = c["H"], c["W"], c["P"], c["views"]
     params = {k: v.to(dev).requires_grad_() for k, v in sc.items()}
     cams_d = {k: v.to(dev) for k, v in cams.items()}
-    dimg = scene.upstream_gradient(3, H, W).to(dev)
+    # the batch loss is a mean over the views of all ranks (pointrix/model/loss.py:27-46): the
+    # upstream gradient of every view carries 1/world
+    dimg = scene.upstream_gradient(3, H, W).to(dev) / world
     r = pb.parse_renderer({"name": "MsplatRender"}, white_bg=True, device=str(dev))
     r.sh_degree = 3
 
@@ -179,13 +198,13 @@ def main():
         for p_ in params.values():
             p_.grad = None
         out = r.render_iter(H, W, cam_src["extrinsic_matrix"][v], cam_src["intrinsic_params"], cam_src["camera_center"][v], **params)
+        rw = parallel.begin_radii_reduce(out["radii"], world)  # final after the forward: hides under the backward
         img = out["rendered_features_split"]["rgb"]
         loss = (img * g_img).sum()
         loss.backward()
         if world > 1:
-            from pointrix_b200 import parallel
-
-            parallel.allreduce_step([p_.grad for p_ in params.values()], out["uv_points"].grad, out["radii"], world)
+            parallel.allreduce_step([p_.grad for p_ in params.values()], out["uv_points"].grad, out["radii"], world,
+                                    average=False, radii_work=rw)
         return loss, out
 
     def sync():
@@ -243,7 +262,7 @@ def main():
     # centre 3) and of its dL/dimg [3,H,W]; device -> host read of the loss and visible count.
     host = {"extrinsic_matrix": cams["extrinsic_matrix"].pin_memory(), "intrinsic_params": cams["intrinsic_params"].pin_memory(),
             "camera_center": cams["camera_center"].pin_memory()}
-    host_dimg = scene.upstream_gradient(3, H, W).pin_memory()
+    host_dimg = (scene.upstream_gradient(3, H, W) / world).pin_memory()
     res_host = torch.zeros(2, dtype=torch.float32).pin_memory()
     h2d = (16 + 4 + 3) * 4 + host_dimg.numel() * 4
     d2h = 8
@@ -264,15 +283,15 @@ def main():
         for p_ in params.values():
             p_.grad = None
         out = r.render_iter(H, W, E, I, Cc, **params)
+        rw = parallel.begin_radii_reduce(out["radii"], world)
         img = out["rendered_features_split"]["rgb"]
         main.wait_stream(copy_stream)
         G.record_stream(main)
         loss = (img * G).sum()
         loss.backward()
         if world > 1:
-            from pointrix_b200 import parallel
-
-            parallel.allreduce_step([p_.grad for p_ in params.values()], out["uv_points"].grad, out["radii"], world)
+            parallel.allreduce_step([p_.grad for p_ in params.values()], out["uv_points"].grad, out["radii"], world,
+                                    average=False, radii_work=rw)
         res = torch.stack([loss.detach(), out["visibility"].sum().float()])
         res_host.copy_(res, non_blocking=True)
         main.synchronize()  # the caller consumes the result every step
@@ -371,7 +390,8 @@ def main():
         line["cpu_baseline"] = cpu_oracle_run(args.config, args.cpu_sample, 2, 1)
     if world == 1 and not args.no_ref_gpu:
         line["ref_gpu"] = ref_gpu_run(args.config, min(K, 10))
-    print(json.dumps(line))
+    print(json.dumps(line), file=out_f)
+    out_f.flush()
     if world > 1:
         dist.destroy_process_group()
 

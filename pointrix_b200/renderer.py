@@ -105,13 +105,16 @@ class _FusedRender(torch.autograd.Function):
         P = pos.shape[0]
         g = _f32(d_out, "dL_drendered")
         grec = torch.zeros(max(P, 1), S, dtype=torch.float32, device=dev)
-        d_pos = torch.empty_like(pos)
-        d_sc = torch.empty_like(sc)
-        d_rot = torch.empty_like(rot)
-        d_op = torch.empty(P, dtype=torch.float32, device=dev)
-        d_sh = torch.empty_like(sh)
+        # every P-sized gradient lives in ONE flat buffer (the 16-byte-aligned blocks first), so a
+        # data-parallel caller exchanges them with a single collective (parallel.allreduce_step)
+        flat = torch.empty(61 * P, dtype=torch.float32, device=dev)
+        d_sh = flat[0:48 * P].view(P, 16, 3)
+        d_rot = flat[48 * P:52 * P].view(P, 4)
+        d_pos = flat[52 * P:55 * P].view(P, 3)
+        d_sc = flat[55 * P:58 * P].view(P, 3)
+        d_op = flat[58 * P:59 * P]
+        d_ndc = flat[59 * P:61 * P].view(P, 2)
         d_extra = torch.empty(P, n_extra, dtype=torch.float32, device=dev) if n_extra > 0 else None
-        d_ndc = torch.empty(P, 2, dtype=torch.float32, device=dev)
         need_cam = any(ctx.needs_input_grad[6:9])
         d_cam = torch.zeros(19, dtype=torch.float32, device=dev) if need_cam else None
         with torch.cuda.device(dev):

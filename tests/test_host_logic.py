@@ -117,3 +117,55 @@ def test_allreduce_step_gloo_world2():
         np.testing.assert_allclose(o1[i], o0[i])
     np.testing.assert_allclose(o0[2], k0[2] + k1[2], rtol=1e-6, atol=1e-6)
     assert (o0[3] == np.maximum(k0[3], k1[3])).all() and (o0[4] == (o0[3] > 0)).all()
+
+
+def _worker_flat(rank, world, port, q):
+    import torch.distributed as dist
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    g = torch.Generator().manual_seed(200 + rank)
+    P = 40
+    flat = torch.randn(61 * P, generator=g)
+    # the fused backward's layout: shs | rotation | position | scaling | opacity | ndc
+    views = [flat[0:48 * P].view(P, 16, 3), flat[48 * P:52 * P].view(P, 4), flat[52 * P:55 * P].view(P, 3),
+             flat[55 * P:58 * P].view(P, 3), flat[58 * P:59 * P].view(P, 1)]
+    ndc = flat[59 * P:61 * P].view(P, 2)
+    assert len(parallel._coalesce(views + [ndc])) == 1  # one collective for the whole set
+    radii = torch.randint(0, 9, (P,), generator=g, dtype=torch.int32)
+    keep = flat.clone()
+    rw = parallel.begin_radii_reduce(radii, world)
+    parallel.allreduce_step(views, ndc, radii, world, average=False, radii_work=rw)
+    q.put((rank, keep.numpy(), flat.numpy(), radii.numpy()))
+    dist.destroy_process_group()
+
+
+def test_allreduce_step_flat_buffer_sum_gloo_world2():
+    """average=False (the loss carries 1/world): the flat gradient buffer of the fused backward goes
+    out as ONE summed all-reduce; radii reduced by the handle started after the forward."""
+    import numpy as np
+    import torch.multiprocessing as mp
+
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() % 2000)
+    ps = [ctx.Process(target=_worker_flat, args=(r, 2, port, q)) for r in range(2)]
+    for p in ps:
+        p.start()
+    res = sorted([q.get(timeout=120) for _ in ps], key=lambda t: t[0])
+    for p in ps:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    (_, k0, o0, r0), (_, k1, o1, r1) = res
+    np.testing.assert_allclose(o0, k0 + k1, rtol=1e-6, atol=1e-6)
+    np.testing.assert_allclose(o1, o0)
+    assert (r0 == r1).all()
+
+
+def test_coalesce_leaves_unrelated_tensors_alone():
+    a, b = torch.zeros(4, 3), torch.zeros(5)
+    out = parallel._coalesce([a, b])
+    assert len(out) == 2
+    flat = torch.zeros(10)
+    gap = parallel._coalesce([flat[0:4], flat[6:10]])  # not contiguous: two collectives
+    assert len(gap) == 2
