@@ -77,11 +77,59 @@ __device__ __forceinline__ void stage_records(float* __restrict__ sm_rec, int* _
         const int j = f / Q, q = f - j * Q;
         if (j < n) {
             const int g = ids[j];
-            if (q == 0) sm_id[j] = g;
+            if (sm_id != nullptr && q == 0) sm_id[j] = g;
             const float4 v = __ldg(reinterpret_cast<const float4*>(rec + (size_t)g * S) + q);
             reinterpret_cast<float4*>(sm_rec)[f] = v;
         }
     }
+}
+
+// shared-memory loads by 32-bit shared address (keeps the window base in one register; the generic
+// form re-materialised it from SR_CgaCtaId on every access)
+__device__ __forceinline__ float4 lds128(unsigned int a) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a) : "memory");
+    return v;
+}
+// stops the compiler from re-deriving a loop-invariant shared address inside the loop
+__device__ __forceinline__ unsigned int opaque_u32(unsigned int x) {
+    unsigned int y;
+    asm volatile("mov.u32 %0, %1;" : "=r"(y) : "r"(x));
+    return y;
+}
+__device__ __forceinline__ unsigned int lds_u16(unsigned int a) {
+    unsigned short v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a) : "memory");
+    return v;
+}
+
+// Per-warp candidate list of one staged batch: the batch entries whose block mask has this warp's bit
+// (and, for the backward, whose list position is below `pos_limit`), in batch order, as u16 indices,
+// padded to a multiple of kUnroll with the index of a never-blending sentinel record.  Returns the
+// padded count.
+constexpr int kUnroll = 4;
+template <bool PAD>
+__device__ __forceinline__ int build_candidates(const unsigned char* __restrict__ sm_mask, unsigned short* __restrict__ list,
+                                                int n, int top, int pos_limit) {
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const unsigned int lt = (1u << lane) - 1u;
+    int cnt = 0;
+    for (int c0 = 0; c0 < n; c0 += 32) {
+        const int jj = c0 + (int)lane;
+        const bool bit = jj < n && (top - 1 - jj) < pos_limit && ((sm_mask[jj] >> warp) & 1u);
+        const unsigned int m = __ballot_sync(0xffffffffu, bit);
+        if (bit) list[cnt + __popc(m & lt)] = (unsigned short)jj;
+        cnt += __popc(m);
+    }
+    const int padded = PAD ? ((cnt + kUnroll - 1) & ~(kUnroll - 1)) : cnt;
+    if (PAD && (int)lane < padded - cnt) list[cnt + lane] = (unsigned short)kBatch;
+    __syncwarp();
+    return padded;
+}
+
+// record slot kBatch of the staging buffer: opacity 0 => alpha 0 => never blended
+__device__ __forceinline__ void write_sentinel(float* sm_rec, int S) {
+    if ((int)threadIdx.x < S) sm_rec[kBatch * S + threadIdx.x] = (threadIdx.x == 2 || threadIdx.x == 4) ? 1.f : 0.f;
 }
 
 template <int CH, int S>
@@ -90,16 +138,18 @@ blend_fwd_kernel(const float* __restrict__ rec, const int* __restrict__ idx_sort
                  float bg, int C, int W, int H, int gx, float* __restrict__ final_T, int* __restrict__ ncontrib,
                  float* __restrict__ out) {
     extern __shared__ __align__(16) float sm_f[];
-    float* sm_rec = sm_f;
-    int* sm_id = reinterpret_cast<int*>(sm_f + kBatch * S);
-    unsigned char* sm_mask = reinterpret_cast<unsigned char*>(sm_id + kBatch);
+    float* sm_rec = sm_f;                                                                  // [kBatch + 1][S]
+    unsigned short* sm_list = reinterpret_cast<unsigned short*>(sm_f + (kBatch + 1) * S);  // [8 warps][kBatch + kUnroll]
+    unsigned char* sm_mask = reinterpret_cast<unsigned char*>(sm_list + (kBlendThreads / 32) * (kBatch + kUnroll));
     const int tile = blockIdx.y * gx + blockIdx.x;
     int lx, ly;
     thread_pixel(lx, ly);
     const int pxi = blockIdx.x * PXB_TILE + lx, pyi = blockIdx.y * PXB_TILE + ly;
-    const float pxf = (float)pxi, pyf = (float)pyi;
     const bool inside = pxi < W && pyi < H;
-    bool done = !inside;
+    const float pxf = (float)pxi, pyf = (float)pyi;
+    // a finished pixel (saturated, or outside the image) raises its alpha threshold above 0.99, the
+    // largest alpha there is: every later pair test fails by itself, the hot loop carries no "done" flag
+    float thr = inside ? 1.0f / 255.0f : 2.0f;
     const int2 range = tile_range[tile];
     int todo = range.y - range.x;
     float T = 1.0f;
@@ -107,13 +157,17 @@ blend_fwd_kernel(const float* __restrict__ rec, const int* __restrict__ idx_sort
     float F[CH];
 #pragma unroll
     for (int k = 0; k < CH; k++) F[k] = 0.f;
-    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const unsigned warp = threadIdx.x >> 5;
     const float X0 = (float)(blockIdx.x * PXB_TILE), Y0 = (float)(blockIdx.y * PXB_TILE);
+    unsigned short* my_list = sm_list + warp * (kBatch + kUnroll);
+    const unsigned int rec_s = opaque_u32((unsigned int)__cvta_generic_to_shared(sm_rec));
+    const unsigned int list_s = opaque_u32((unsigned int)__cvta_generic_to_shared(my_list));
+    write_sentinel(sm_rec, S);
 
     for (int base = 0; todo > 0; base += kBatch, todo -= kBatch) {
-        if (__syncthreads_count(done) == kBlendThreads) break;
+        if (__syncthreads_count(thr > 1.f) == kBlendThreads) break;
         const int n = min(kBatch, todo);
-        stage_records<S>(sm_rec, sm_id, rec, idx_sorted + range.x + base, n);
+        stage_records<S>(sm_rec, nullptr, rec, idx_sorted + range.x + base, n);
         __syncthreads();
         if ((int)threadIdx.x < n) {
             const float4 r0 = *reinterpret_cast<const float4*>(sm_rec + threadIdx.x * S);
@@ -121,38 +175,42 @@ blend_fwd_kernel(const float* __restrict__ rec, const int* __restrict__ idx_sort
             sm_mask[threadIdx.x] = (unsigned char)block_mask(r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, X0, Y0);
         }
         __syncthreads();
-        if (__all_sync(0xffffffffu, done)) continue;  // whole warp saturated: it only helps staging
-        for (int c0 = 0; c0 < n; c0 += 32) {
-            const int jj = c0 + (int)lane;
-            unsigned int m = __ballot_sync(0xffffffffu, jj < n && ((sm_mask[jj] >> warp) & 1u));
-            PXB_STAT(5, __popc(m));
-            while (m) {
-                const int j = c0 + __ffs(m) - 1;
-                m &= m - 1;
-                if (done) continue;
-                const float4 r0 = *reinterpret_cast<const float4*>(sm_rec + j * S);      // u v A B
-                const float4 r1 = *reinterpret_cast<const float4*>(sm_rec + j * S + 4);  // C op f0 f1
+        if (__all_sync(0xffffffffu, thr > 1.f)) continue;  // whole warp saturated: it only helps staging
+        const int cnt = build_candidates<true>(sm_mask, my_list, n, 0x40000000, 0x7fffffff);
+        PXB_STAT(5, cnt);
+        const int last_base = base + 1;
+        for (int c = 0; c < cnt; c += kUnroll) {
+#pragma unroll
+            for (int u = 0; u < kUnroll; u++) {
+                const int j = (int)lds_u16(list_s + 2u * (unsigned)(c + u));
+                const unsigned int ra = rec_s + (unsigned)j * (S * 4u);
+                const float4 r0 = lds128(ra);        // u v A B
+                const float4 r1 = lds128(ra + 16u);  // C op f0 f1
                 const float dx = __fadd_rn(r0.x, -pxf), dy = __fadd_rn(r0.y, -pyf);
                 const float power = blend_power(dx, dy, r0.z, r0.w, r1.x);
-                if (power > 0.f) continue;
                 const float alpha = fmin_nn(__fmul_rn(r1.y, blend_G(power)), 0.99f);
-                if (alpha < 1.0f / 255.0f) continue;
-                const float next_T = __fmul_rn(T, __fadd_rn(-alpha, 1.0f));
-                if (next_T < 0.0001f) { done = true; continue; }
-                F[0] = __fmaf_rn(T, __fmul_rn(alpha, r1.z), F[0]);
-                if (CH > 1) F[1] = __fmaf_rn(T, __fmul_rn(alpha, r1.w), F[1]);
+                // the reference's two skips (alpha_blending.cu:81-88) as one predicate
+                if (power <= 0.f && alpha >= thr) {
+                    const float next_T = __fmul_rn(T, __fadd_rn(-alpha, 1.0f));
+                    if (next_T < 0.0001f) {
+                        thr = 2.0f;  // done: this Gaussian is NOT blended
+                    } else {
+                        F[0] = __fmaf_rn(T, __fmul_rn(alpha, r1.z), F[0]);
+                        if (CH > 1) F[1] = __fmaf_rn(T, __fmul_rn(alpha, r1.w), F[1]);
 #pragma unroll
-                for (int q = 2; q < CH; q += 4) {
-                    const float4 rf = *reinterpret_cast<const float4*>(sm_rec + j * S + 6 + q);
-                    F[q] = __fmaf_rn(T, __fmul_rn(alpha, rf.x), F[q]);
-                    if (q + 1 < CH) F[q + 1] = __fmaf_rn(T, __fmul_rn(alpha, rf.y), F[q + 1]);
-                    if (q + 2 < CH) F[q + 2] = __fmaf_rn(T, __fmul_rn(alpha, rf.z), F[q + 2]);
-                    if (q + 3 < CH) F[q + 3] = __fmaf_rn(T, __fmul_rn(alpha, rf.w), F[q + 3]);
+                        for (int q = 2; q < CH; q += 4) {
+                            const float4 rf = lds128(ra + 4u * (6 + q));
+                            F[q] = __fmaf_rn(T, __fmul_rn(alpha, rf.x), F[q]);
+                            if (q + 1 < CH) F[q + 1] = __fmaf_rn(T, __fmul_rn(alpha, rf.y), F[q + 1]);
+                            if (q + 2 < CH) F[q + 2] = __fmaf_rn(T, __fmul_rn(alpha, rf.z), F[q + 2]);
+                            if (q + 3 < CH) F[q + 3] = __fmaf_rn(T, __fmul_rn(alpha, rf.w), F[q + 3]);
+                        }
+                        T = next_T;
+                        last = last_base + j;  // 1-based list position of the last blended Gaussian (ncontrib)
+                    }
                 }
-                T = next_T;
-                last = base + j + 1;  // 1-based list position of the last blended Gaussian (ncontrib)
             }
-            if (__all_sync(0xffffffffu, done)) break;
+            if (__all_sync(0xffffffffu, thr > 1.f)) break;
         }
     }
     if (inside) {
@@ -199,7 +257,8 @@ blend_bwd_kernel(const float* __restrict__ rec, const int* __restrict__ idx_sort
     float* sm_dpix = sm_rec + kBatch * S;                               // [NW][32][CHP]
     float2* sm_slot = reinterpret_cast<float2*>(sm_dpix + NW * 32 * CHP);  // [NW][kSlots][kSlotPitch]
     int* sm_id = reinterpret_cast<int*>(sm_slot + NW * kSlots * kSlotPitch);  // [kBatch]
-    unsigned char* sm_mask = reinterpret_cast<unsigned char*>(sm_id + kBatch);  // [kBatch]
+    unsigned short* sm_list = reinterpret_cast<unsigned short*>(sm_id + kBatch);  // [NW][kBatch]
+    unsigned char* sm_mask = reinterpret_cast<unsigned char*>(sm_list + NW * kBatch);  // [kBatch]
     const int tile = blockIdx.y * gx + blockIdx.x;
     int lx, ly;
     thread_pixel(lx, ly);
@@ -243,6 +302,9 @@ blend_bwd_kernel(const float* __restrict__ rec, const int* __restrict__ idx_sort
     const float by = Y0 + (float)(((warp >> 1) << 2) + 2 * my_half);
     int nslot = 0;   // warp-uniform
     int my_j = 0;    // batch entry parked in my_slot
+    unsigned short* my_list = sm_list + warp * kBatch;
+    const unsigned int rec_s = opaque_u32((unsigned int)__cvta_generic_to_shared(sm_rec));
+    const unsigned int list_s = opaque_u32((unsigned int)__cvta_generic_to_shared(my_list));
 
     auto flush = [&](int n) {
         __syncwarp();
@@ -326,55 +388,48 @@ blend_bwd_kernel(const float* __restrict__ rec, const int* __restrict__ idx_sort
             sm_mask[threadIdx.x] = (unsigned char)block_mask(r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, X0, Y0);
         }
         __syncthreads();
-        for (int c0 = 0; c0 < n; c0 += 32) {
-            const int jj = c0 + (int)lane;
-            // positions >= warp_last contribute to no pixel of this warp
-            unsigned int m = __ballot_sync(0xffffffffu, jj < n && (top - 1 - jj) < warp_last && ((sm_mask[jj] >> warp) & 1u));
-            PXB_STAT(0, __popc(m));
-            while (m) {
-                const int j = c0 + __ffs(m) - 1;
-                m &= m - 1;
-                const int pos = top - 1 - j;  // list position of this entry
-                bool valid = pos < last;
-                float G = 0.f, alpha = 0.f;
-                const float4 r0 = *reinterpret_cast<const float4*>(sm_rec + j * S);
-                const float4 r1 = *reinterpret_cast<const float4*>(sm_rec + j * S + 4);
-                if (valid) {
-                    const float dx = __fadd_rn(r0.x, -pxf), dy = __fadd_rn(r0.y, -pyf);
-                    const float power = blend_power(dx, dy, r0.z, r0.w, r1.x);
-                    G = blend_G(power);
-                    alpha = fmin_nn(__fmul_rn(r1.y, G), 0.99f);
-                    valid = !(power > 0.f) && !(alpha < 1.0f / 255.0f);
-                }
-                const unsigned int vm = __ballot_sync(0xffffffffu, valid);
-                if (vm == 0u) continue;
-                PXB_STAT(1, 1); PXB_STAT(2, __popc(vm));
-                float2 qw = make_float2(0.f, 0.f);
-                if (valid) {
-                    const float ra = __fdividef(1.f, 1.f - alpha);
-                    T = T * ra;
-                    qw.y = alpha * T;
-                    float dL_dalpha = 0.f;
+        // positions >= warp_last contribute to no pixel of this warp
+        const int cnt = build_candidates<false>(sm_mask, my_list, n, top, warp_last);
+        PXB_STAT(0, cnt);
+        for (int c = 0; c < cnt; c++) {
+            const int j = (int)lds_u16(list_s + 2u * (unsigned)c);
+            const unsigned int ra = rec_s + (unsigned)j * (S * 4u);
+            const int pos = top - 1 - j;  // list position of this entry
+            const float4 r0 = lds128(ra);        // u v A B
+            const float4 r1 = lds128(ra + 16u);  // C op f0 f1
+            const float dx = __fadd_rn(r0.x, -pxf), dy = __fadd_rn(r0.y, -pyf);
+            const float power = blend_power(dx, dy, r0.z, r0.w, r1.x);
+            const float G = blend_G(power);
+            const float alpha = fmin_nn(__fmul_rn(r1.y, G), 0.99f);
+            const bool valid = pos < last && power <= 0.f && alpha >= 1.0f / 255.0f;
+            const unsigned int vm = __ballot_sync(0xffffffffu, valid);
+            if (vm == 0u) continue;
+            PXB_STAT(1, 1); PXB_STAT(2, __popc(vm));
+            float2 qw = make_float2(0.f, 0.f);
+            if (valid) {
+                const float ra1 = __fdividef(1.f, 1.f - alpha);
+                T = T * ra1;
+                qw.y = alpha * T;
+                float dL_dalpha = 0.f;
 #pragma unroll
-                    for (int k = 0; k < CH; k++) {
-                        const float f = (k == 0) ? r1.z : (k == 1) ? r1.w : sm_rec[j * S + 6 + k];
-                        accum[k] = last_alpha * lastf[k] + (1.f - last_alpha) * accum[k];
-                        lastf[k] = f;
-                        dL_dalpha += (f - accum[k]) * dpix[k];
-                    }
-                    dL_dalpha *= T;
-                    last_alpha = alpha;
-                    dL_dalpha += (-T_final * ra) * bg_dot;
-                    qw.x = G * dL_dalpha;
+                for (int k = 0; k < CH; k++) {
+                    const float f = (k == 0) ? r1.z : (k == 1) ? r1.w : sm_rec[j * S + 6 + k];
+                    accum[k] = last_alpha * lastf[k] + (1.f - last_alpha) * accum[k];
+                    lastf[k] = f;
+                    dL_dalpha += (f - accum[k]) * dpix[k];
                 }
-                slots[nslot * kSlotPitch + lane] = qw;
-                if (my_slot == nslot) my_j = j;
-                nslot++;
-                if (nslot == kSlots) {
-                    PXB_STAT(3, 1);
-                    flush(kSlots);
-                    nslot = 0;
-                }
+                dL_dalpha *= T;
+                last_alpha = alpha;
+                dL_dalpha += (-T_final * ra1) * bg_dot;
+                qw.x = G * dL_dalpha;
+            }
+            slots[nslot * kSlotPitch + lane] = qw;
+            if (my_slot == nslot) my_j = j;
+            nslot++;
+            if (nslot == kSlots) {
+                PXB_STAT(3, 1);
+                flush(kSlots);
+                nslot = 0;
             }
         }
         if (nslot) {  // the batch buffer is about to be restaged: drain
@@ -421,7 +476,7 @@ template <int CH, int S>
 static int launch_fwd(const float* rec, const int* idx_sorted, const int* tile_range, float bg, int C, int W, int H,
                       float* final_T, int* ncontrib, float* out, cudaStream_t s) {
     const int gx = (W + PXB_TILE - 1) / PXB_TILE, gy = (H + PXB_TILE - 1) / PXB_TILE;
-    const size_t smem = (size_t)kBatch * S * 4 + kBatch * 4 + kBatch;
+    const size_t smem = (size_t)(kBatch + 1) * S * 4 + (kBlendThreads / 32) * (kBatch + kUnroll) * 2 + kBatch;
     static bool attr = false;
     if (!attr) {
         if (smem > 48 * 1024)
@@ -440,7 +495,7 @@ static int launch_bwd(const float* rec, const int* idx_sorted, const int* tile_r
                       const float* final_T, const int* ncontrib, const float* dL_dout, float* grec, cudaStream_t s) {
     const int gx = (W + PXB_TILE - 1) / PXB_TILE, gy = (H + PXB_TILE - 1) / PXB_TILE;
     constexpr int CHP = (CH + 3) & ~3, NW = kBlendThreads / 32;
-    const size_t smem = (size_t)(kBatch * S + NW * 32 * CHP + 2 * NW * kSlots * kSlotPitch) * 4 + kBatch * 4 + kBatch;
+    const size_t smem = (size_t)(kBatch * S + NW * 32 * CHP + 2 * NW * kSlots * kSlotPitch) * 4 + kBatch * 4 + NW * kBatch * 2 + kBatch;
     static bool attr = false;
     if (!attr) {
         if (smem > 48 * 1024)
