@@ -272,17 +272,16 @@ blend_bwd_kernel(const float* __restrict__ rec, const int* __restrict__ idx_sort
     const float T_final = inside ? final_T[pix] : 0.f;
     float T = T_final;
     const int last = inside ? ncontrib[pix] : 0;
-    float accum[CH], dpix[CH], lastf[CH];
+    float dpix[CH];
     float bg_dot = 0.f;
     float* my_dpix = sm_dpix + (warp * 32 + lane) * CHP;
 #pragma unroll
     for (int k = 0; k < CH; k++) {
-        accum[k] = 0.f; lastf[k] = 0.f;
         dpix[k] = (inside && k < C) ? dL_dout[(size_t)k * H * W + pix] : 0.f;
         bg_dot += bg * dpix[k];
         my_dpix[k] = dpix[k];
     }
-    float last_alpha = 0.f;
+    float Bacc = T_final * bg_dot;  // see the pair loop
     // the deepest contributor of any pixel of the CTA / of this warp bounds the work: list entries
     // at positions >= that bound were never blended by these pixels
     const int warp_last = __reduce_max_sync(0xffffffffu, last);
@@ -407,20 +406,20 @@ blend_bwd_kernel(const float* __restrict__ rec, const int* __restrict__ idx_sort
             PXB_STAT(1, 1); PXB_STAT(2, __popc(vm));
             float2 qw = make_float2(0.f, 0.f);
             if (valid) {
+                // dL/dalpha = T * <f - accum, dpix> - T_final/(1-alpha) * bg * sum(dpix)   (alpha_blending.cu:206-222)
+                // with accum the normalised colour behind this Gaussian.  Only dot products with the
+                // pixel's dL/dpix enter, so the colour recurrence collapses to ONE scalar per pixel:
+                //   B = T_final*bg*sum(dpix) + sum_{behind} alpha_j T_j <f_j, dpix>,
+                //   dL/dalpha = T <f, dpix> - B / (1 - alpha).
                 const float ra1 = __fdividef(1.f, 1.f - alpha);
                 T = T * ra1;
                 qw.y = alpha * T;
-                float dL_dalpha = 0.f;
+                float fd = r1.z * dpix[0];
+                if (CH > 1) fd = fmaf(r1.w, dpix[1], fd);
 #pragma unroll
-                for (int k = 0; k < CH; k++) {
-                    const float f = (k == 0) ? r1.z : (k == 1) ? r1.w : sm_rec[j * S + 6 + k];
-                    accum[k] = last_alpha * lastf[k] + (1.f - last_alpha) * accum[k];
-                    lastf[k] = f;
-                    dL_dalpha += (f - accum[k]) * dpix[k];
-                }
-                dL_dalpha *= T;
-                last_alpha = alpha;
-                dL_dalpha += (-T_final * ra1) * bg_dot;
+                for (int k = 2; k < CH; k++) fd = fmaf(sm_rec[j * S + 6 + k], dpix[k], fd);
+                const float dL_dalpha = fmaf(T, fd, -(ra1 * Bacc));
+                Bacc = fmaf(qw.y, fd, Bacc);
                 qw.x = G * dL_dalpha;
             }
             slots[nslot * kSlotPitch + lane] = qw;
