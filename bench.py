@@ -335,7 +335,9 @@ def _main(out_f):
             cov = ops.compute_cov3d(params["scaling"], params["rotation"], vis)
             _, _, tl = ops.ewa_project(params["position"], cov, cams_d["intrinsic_params"], cams_d["extrinsic_matrix"][v][:3].contiguous(), uv, W, H, vis)
             Ns.append(int(tl.sum()))
-    N_mean = sum(Ns) / len(Ns)
+    N_ref = sum(Ns) / len(Ns)  # length of the reference's tile lists (3-sigma squares)
+    # the fused path bins only the tiles the alpha >= 1/255 ellipse reaches: its own count drives the traffic
+    N_mean = float(ops.LAST_N.get((dev.index, True), N_ref))
     Cch, S = 3, 12
     tiles = ((W + 15) // 16) * ((H + 15) // 16)
     passes = max(1, ((tiles - 1).bit_length() + 7) // 8)
@@ -378,7 +380,8 @@ def _main(out_f):
         "metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W_,
         "ms_per_step": round(ms / K, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(args.config), "intersections_mean": N_mean,
+        "config": {"workload": workload_name(args.config), "intersections_reference_lists": N_ref,
+                   "intersections_binned": N_mean,
                    "parallelism": f"view-sharded dp{world}" + (", NCCL all-reduce of 59+2 floats/Gaussian + max(radii) per step" if world > 1 else ""),
                    "cache": "inputs larger than L2 (236 MB Gaussian table + 48 MB records vs 126 MB L2); a different view every step"},
         "render_mpix_s": round(render_mpix, 2),

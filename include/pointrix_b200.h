@@ -87,9 +87,13 @@ int pxb_bin_prepare(int P, const float* depth, const int* radius, const int* til
  * capacity: grids/buffers are sized for N, the kernels process min(*total_dev, N) entries and the caller
  * verifies *total_dev <= N afterwards (re-running with more capacity if not) -- no host round trip.
  * uv may be strided (uv_stride floats between Gaussians) so the packed record can be passed.
+ * tight != 0 (fused render path only; uv must then be the packed record): emit only the tiles of the
+ * reference rectangle that the alpha >= 1/255 ellipse can reach -- `tiles` must hold those counts
+ * (pxb_fused_forward with tight != 0).  Images and gradients are unchanged; idx_sorted / tile_range
+ * are then NOT the reference's arrays (use tight = 0 for those).
  * idx_sorted[N] i32, tile_range[tiles,2] i32; keys_sorted_out[N] i64 optional (NULL to skip; exact-N mode only). */
-int pxb_sort_gaussian(int P, long long N, const int* total_dev, const float* uv, int uv_stride, const float* depth,
-                      const int* radius, const int* tiles, int W, int H, int* idx_sorted, int* tile_range,
+int pxb_sort_gaussian(int P, long long N, const int* total_dev, const float* uv, int uv_stride, int tight,
+                      const float* depth, const int* radius, const int* tiles, int W, int H, int* idx_sorted, int* tile_range,
                       long long* keys_sorted_out, void* ws_p, size_t ws_p_bytes, void* ws_n, size_t ws_n_bytes,
                       void* stream);
 
@@ -115,7 +119,7 @@ int pxb_blend_backward(const float* rec, int S, int C, const int* idx_sorted, co
 int pxb_fused_forward(int P, int sh_degree, const float* pos, const float* scales, const float* quats,
                       const float* opacity, const float* shs, const float* extra, int n_extra, int with_depth,
                       const float* intr, const float* extr, const float* cam_center, int W, int H, float nearest,
-                      float extent, int S, float* rec, float* depth, int* radius, int* tiles, void* stream);
+                      float extent, int S, int tight, float* rec, float* depth, int* radius, int* tiles, void* stream);
 int pxb_fused_backward(int P, int sh_degree, const float* pos, const float* scales, const float* quats,
                        const float* shs, int n_extra, int with_depth, const float* intr, const float* extr,
                        const float* cam_center, int W, int H, int S, const float* depth, const int* radius,

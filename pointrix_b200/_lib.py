@@ -33,13 +33,13 @@ SIGNATURES = {
     "pxb_bin_prepare_workspace_bytes": (sz, [i32]),
     "pxb_bin_sort_workspace_bytes": (sz, [i64, i32, i32]),
     "pxb_bin_prepare": (i32, [i32, p, p, p, p, p, sz, p]),
-    "pxb_sort_gaussian": (i32, [i32, i64, p, p, i32, p, p, p, i32, i32, p, p, p, p, sz, p, sz, p]),
+    "pxb_sort_gaussian": (i32, [i32, i64, p, p, i32, i32, p, p, p, i32, i32, p, p, p, p, sz, p, sz, p]),
     "pxb_record_stride": (i32, [i32]),
     "pxb_pack_records": (i32, [i32, p, p, p, p, i32, i32, i32, i32, p, p]),
     "pxb_unpack_grads": (i32, [i32, p, i32, i32, i32, i32, i32, p, p, p, p, p]),
     "pxb_blend_forward": (i32, [p, i32, i32, p, p, f32, i32, i32, p, p, p, p]),
     "pxb_blend_backward": (i32, [p, i32, i32, p, p, f32, i32, i32, p, p, p, p, p]),
-    "pxb_fused_forward": (i32, [i32, i32, p, p, p, p, p, p, i32, i32, p, p, p, i32, i32, f32, f32, i32, p, p, p, p, p]),
+    "pxb_fused_forward": (i32, [i32, i32, p, p, p, p, p, p, i32, i32, p, p, p, i32, i32, f32, f32, i32, i32, p, p, p, p, p]),
     "pxb_fused_backward": (i32, [i32, i32, p, p, p, p, i32, i32, p, p, p, i32, i32, i32, p, p, p, p, p, p, p, p, p, p, p, p]),
 }
 
@@ -118,7 +118,7 @@ def launch(name: str, *args) -> None:
     fn = getattr(lib, name)
     n = KERNELS_PER_CALL.get(name, 1)
     if name == "pxb_sort_gaussian":
-        W, H = args[8], args[9]
+        W, H = args[9], args[10]
         nt = ((W + 15) // 16) * ((H + 15) // 16)
         n = (2 + 3 * max(1, (max(nt - 1, 0).bit_length() + 7) // 8)) if args[1] > 0 else 0
     launch_count += n

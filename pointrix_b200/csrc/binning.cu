@@ -120,8 +120,8 @@ constexpr int kEmitThreads = 256;
 __global__ void __launch_bounds__(kEmitThreads)
 emit_keys_kernel(int P, const float* __restrict__ uv, int uv_stride, const int* __restrict__ radius,
                  const int* __restrict__ tiles, const unsigned int* __restrict__ order,
-                 const int* __restrict__ offs_incl, int gx, int gy, long long N_cap, const int* __restrict__ n_dev,
-                 unsigned int* __restrict__ keys, unsigned int* __restrict__ vals) {
+                 const int* __restrict__ offs_incl, int gx, int gy, int tight, long long N_cap,
+                 const int* __restrict__ n_dev, unsigned int* __restrict__ keys, unsigned int* __restrict__ vals) {
     const long long N = n_dev ? min((long long)*n_dev, N_cap) : N_cap;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
@@ -131,7 +131,11 @@ emit_keys_kernel(int P, const float* __restrict__ uv, int uv_stride, const int* 
         const int r = radius[g];
         if (r > 0) {
             int x1, y1;
-            tile_rect(uv[(size_t)g * uv_stride], uv[(size_t)g * uv_stride + 1], r, gx, gy, x0, y0, x1, y1);
+            const float* rg = uv + (size_t)g * uv_stride;
+            if (tight)  // uv is the packed blend record {u,v,A,B,C,op,...}: the fused path's rectangle
+                tight_tile_rect(rg[0], rg[1], r, rg[2], rg[3], rg[4], rg[5], gx, gy, x0, y0, x1, y1);
+            else
+                tile_rect(rg[0], rg[1], r, gx, gy, x0, y0, x1, y1);
             w = max(x1 - x0, 1);
             cnt = tiles[g];  // == w * (y1 - y0) (ewa_project.cu:81); the scan used the same count
             off = offs_incl[i] - cnt;
@@ -583,8 +587,8 @@ int pxb_bin_prepare(int P, const float* depth, const int* radius, const int* til
 
 // keys + tile sort + ranges.  N: exact count when total_dev == NULL, else a capacity: the kernels
 // then process min(*total_dev, N) intersections and the caller verifies *total_dev <= N afterwards.
-int pxb_sort_gaussian(int P, long long N, const int* total_dev, const float* uv, int uv_stride, const float* depth,
-                      const int* radius, const int* tiles, int W, int H, int* idx_sorted, int* tile_range,
+int pxb_sort_gaussian(int P, long long N, const int* total_dev, const float* uv, int uv_stride, int tight,
+                      const float* depth, const int* radius, const int* tiles, int W, int H, int* idx_sorted, int* tile_range,
                       long long* keys_sorted_out /*nullable, [N]*/, void* ws_p, size_t ws_p_bytes, void* ws_n,
                       size_t ws_n_bytes, void* stream) {
     cudaStream_t s = (cudaStream_t)stream;
@@ -592,7 +596,7 @@ int pxb_sort_gaussian(int P, long long N, const int* total_dev, const float* uv,
     const int num_tiles = gx * gy;
     PXB_CUDA_OK(cudaMemsetAsync(tile_range, 0, (size_t)num_tiles * 2 * sizeof(int), s));
     if (P <= 0 || N <= 0) return 0;
-    if (N > 0x3fffffffll) return PXB_ERR_BAD_ARG;
+    if (N > 0x3fffffffll || (tight && uv_stride < 6)) return PXB_ERR_BAD_ARG;
     WsP bp = carve_p(ws_p, P);
     WsN bn = carve_n(ws_n, N, num_tiles);
     if (ws_p_bytes < bp.total || ws_n_bytes < bn.total) return PXB_ERR_WORKSPACE;
@@ -603,7 +607,7 @@ int pxb_sort_gaussian(int P, long long N, const int* total_dev, const float* uv,
     v[passes & 1] = (unsigned int*)idx_sorted;
     v[(passes + 1) & 1] = bn.vals_tmp;
     emit_keys_kernel<<<(P + kEmitThreads - 1) / kEmitThreads, kEmitThreads, 0, s>>>(
-        P, uv, uv_stride, radius, tiles, bp.vals[0], bp.offsets, gx, gy, N, total_dev, k[0], v[0]);
+        P, uv, uv_stride, radius, tiles, bp.vals[0], bp.offsets, gx, gy, tight, N, total_dev, k[0], v[0]);
     int rc = radix_sort_u32(k, v, (int)N, total_dev, tile_bits(num_tiles), bn.counts, bn.totals, s);
     if (rc) return rc;
     const unsigned int* tile_sorted = k[passes & 1];

@@ -188,6 +188,32 @@ __device__ __forceinline__ void tile_rect(float u, float v, int radius, int gx, 
     y1 = min(max(0, __float2int_rz(__fmul_rn(__fadd_rn(__fadd_rn(__fadd_rn(v, rf), 16.0f), -1.0f), 0.0625f))), gy);
 }
 
+// Tile rectangle of the fused render path: the reference rectangle intersected with the tiles that
+// the alpha >= 1/255 ellipse can reach.  A pixel passes the reference's skip rules only if
+// op*exp(-q/2) >= 1/255, q = A dx^2 + 2B dx dy + C dy^2, i.e. q <= 2 ln(255 op); the bounding box of
+// that ellipse has half extents sqrt(k C/det), sqrt(k A/det).  k is inflated by 1 % + 0.02 and the box
+// by half a pixel, which dwarfs the MUFU approximation error: no tile holding a pixel the exact test
+// would blend is dropped, so images and gradients are unchanged while the intersection count falls
+// by the ratio of the two boxes.  Tile c holds pixel centres 16c .. 16c+15.
+__device__ __forceinline__ void tight_tile_rect(float u, float v, int radius, float A, float B, float C, float op,
+                                                int gx, int gy, int& x0, int& y0, int& x1, int& y1) {
+    tile_rect(u, v, radius, gx, gy, x0, y0, x1, y1);
+    if (op < 1.0f / 255.0f) { x1 = x0; y1 = y0; return; }  // alpha <= op < 1/255 at every pixel
+    const float det = A * C - B * B;
+    if (!(det > 0.f) || !(A > 0.f) || !(C > 0.f)) return;
+    const float k = 2.02f * __logf(255.0f * op) + 0.02f;
+    const float inv = 1.0f / det;
+    const float hx = sqrtf(k * C * inv) + 0.51f, hy = sqrtf(k * A * inv) + 0.51f;
+    if (!(hx == hx) || !(hy == hy) || hx > 1e6f || hy > 1e6f) return;
+    const float lim = 1e7f;
+    const int cx0 = (int)ceilf(fminf(fmaxf((u - hx - 15.f) * 0.0625f, -lim), lim));
+    const int cx1 = (int)floorf(fminf(fmaxf((u + hx) * 0.0625f, -lim), lim)) + 1;
+    const int cy0 = (int)ceilf(fminf(fmaxf((v - hy - 15.f) * 0.0625f, -lim), lim));
+    const int cy1 = (int)floorf(fminf(fmaxf((v + hy) * 0.0625f, -lim), lim)) + 1;
+    x0 = max(x0, cx0); x1 = max(min(x1, cx1), x0);
+    y0 = max(y0, cy0); y1 = max(min(y1, cy1), y0);
+}
+
 // radius / conic / tiles from (a,b,c) (ewa_project.cu:60-82).  Returns false if
 // the Gaussian is dropped (det == 0 or empty rect): outputs stay zero.
 __device__ __forceinline__ bool ewa_finish(float a, float b, float c, float u, float v, int gx, int gy,

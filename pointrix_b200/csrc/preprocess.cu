@@ -427,7 +427,7 @@ fused_fwd_kernel(int P, const float* __restrict__ pos, const float* __restrict__
                  const float* __restrict__ shs /*[P,16,3]*/, const float* __restrict__ extra, int n_extra,
                  int with_depth, const float* __restrict__ intr, const float* __restrict__ extr,
                  const float* __restrict__ cam_center, int W, int H, int gx, int gy, float nearest,
-                 float extent, int S, float* __restrict__ rec, float* __restrict__ depth,
+                 float extent, int S, int tight, float* __restrict__ rec, float* __restrict__ depth,
                  int* __restrict__ radius, int* __restrict__ tiles) {
     extern __shared__ __align__(16) float sh_smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -492,12 +492,18 @@ fused_fwd_kernel(int P, const float* __restrict__ pos, const float* __restrict__
     // culled Gaussians: uv = 0, depth = 0, as project_point leaves them
     const float dep = keep ? t.z : 0.f;
     if (!keep) { u = 0.f; v = 0.f; }
+    const float op_i = opacity[i];
+    if (tight && rad > 0) {  // count only the tiles the alpha >= 1/255 ellipse can reach (common.cuh)
+        int x0, y0, x1, y1;
+        tight_tile_rect(u, v, rad, cn[0], cn[1], cn[2], op_i, gx, gy, x0, y0, x1, y1);
+        nt = (x1 - x0) * (y1 - y0);
+    }
     depth[i] = dep;
     radius[i] = rad;
     tiles[i] = nt;
     float* r = rec + (size_t)i * S;
     *reinterpret_cast<float4*>(r) = make_float4(u, v, cn[0], cn[1]);
-    *reinterpret_cast<float4*>(r + 4) = make_float4(cn[2], opacity[i], rgb[0], rgb[1]);
+    *reinterpret_cast<float4*>(r + 4) = make_float4(cn[2], op_i, rgb[0], rgb[1]);
     // remaining feature columns: rgb[2], [depth], extra[P,n_extra], zero pad
     auto feat = [&](int f) -> float {
         if (f == 2) return rgb[2];
@@ -767,7 +773,7 @@ int pxb_init(void) {
 int pxb_fused_forward(int P, int sh_degree, const float* pos, const float* scales, const float* quats,
                       const float* opacity, const float* shs, const float* extra, int n_extra, int with_depth,
                       const float* intr, const float* extr, const float* cam_center, int W, int H, float nearest,
-                      float extent, int S, float* rec, float* depth, int* radius, int* tiles, void* stream) {
+                      float extent, int S, int tight, float* rec, float* depth, int* radius, int* tiles, void* stream) {
     if (P <= 0) return 0;
     if (sh_degree < 0 || sh_degree > 3) return PXB_ERR_UNSUPPORTED;
     if (S % 4 != 0 || S < 6 + 3 + with_depth + n_extra) return PXB_ERR_BAD_ARG;
@@ -779,7 +785,7 @@ int pxb_fused_forward(int P, int sh_degree, const float* pos, const float* scale
 #define PXB_LAUNCH_FWD(KA)                                                                                         \
     fused_fwd_kernel<KA><<<nb, kFThreads, smem, s>>>(P, pos, scales, (const float4*)quats, opacity, shs, extra,    \
                                                      n_extra, with_depth, intr, extr, cam_center, W, H, gx, gy,    \
-                                                     nearest, extent, S, rec, depth, radius, tiles)
+                                                     nearest, extent, S, tight, rec, depth, radius, tiles)
     switch (sh_degree) {
         case 0: PXB_LAUNCH_FWD(1); break;
         case 1: PXB_LAUNCH_FWD(4); break;

@@ -204,7 +204,7 @@ def _prepare(depth: Tensor, radius: Tensor, tiles: Tensor, stream):
 
 
 def _bin(uv_like: Tensor, uv_stride: int, depth: Tensor, radius: Tensor, tiles: Tensor, W: int, H: int,
-         return_keys: bool = False):
+         return_keys: bool = False, tight: bool = False):
     dev = depth.device
     P = radius.numel()
     n_tiles = ((W + TILE - 1) // TILE) * ((H + TILE - 1) // TILE)
@@ -213,11 +213,12 @@ def _bin(uv_like: Tensor, uv_stride: int, depth: Tensor, radius: Tensor, tiles: 
         stream = _stream(dev)
         total, ws_p, ws_p_bytes = _prepare(depth, radius, tiles, stream)
         N = int(total.item())  # the one host sync of the operator path (the reference has two)
+        LAST_N[(dev.index, bool(tight))] = N
         idx_sorted = torch.empty(N, dtype=torch.int32, device=dev)
         keys = torch.empty(N, dtype=torch.int64, device=dev) if return_keys else None
         ws_n_bytes = lib.pxb_bin_sort_workspace_bytes(max(N, 1), int(W), int(H))
         ws_n = torch.empty(ws_n_bytes, dtype=torch.uint8, device=dev)
-        launch("pxb_sort_gaussian", P, N, _p(None), _p(uv_like), uv_stride, _p(depth), _p(radius), _p(tiles), int(W), int(H),
+        launch("pxb_sort_gaussian", P, N, _p(None), _p(uv_like), uv_stride, int(tight), _p(depth), _p(radius), _p(tiles), int(W), int(H),
                _p(idx_sorted), _p(tile_range), _p(keys), _p(ws_p), ws_p_bytes, _p(ws_n), ws_n_bytes, stream)
     if return_keys:
         return idx_sorted, tile_range, keys
@@ -227,9 +228,11 @@ def _bin(uv_like: Tensor, uv_stride: int, depth: Tensor, radius: Tensor, tiles: 
 # capacity of the sync-free binning per (device, P, W, H): learnt from the previous views
 _CAPACITY = {}
 _PINNED = {}
+LAST_N = {}  # (device index, tight) -> intersection count of the most recent binning (diagnostics / bench)
 
 
-def _bin_nosync(uv_like: Tensor, uv_stride: int, depth: Tensor, radius: Tensor, tiles: Tensor, W: int, H: int):
+def _bin_nosync(uv_like: Tensor, uv_stride: int, depth: Tensor, radius: Tensor, tiles: Tensor, W: int, H: int,
+                tight: bool = False):
     """Binning without a host round trip on the critical path (fused plugin path).
 
     Buffers and grids are sized for a capacity learnt from earlier views; the kernels read the
@@ -239,10 +242,10 @@ def _bin_nosync(uv_like: Tensor, uv_stride: int, depth: Tensor, radius: Tensor, 
     the exact count if the capacity was exceeded (the caller then re-bins and re-blends; rare)."""
     dev = depth.device
     P = radius.numel()
-    key = (dev.index, P, int(W), int(H))
+    key = (dev.index, P, int(W), int(H), bool(tight))
     cap = _CAPACITY.get(key)
     if cap is None or P == 0:
-        idx_sorted, tile_range = _bin(uv_like, uv_stride, depth, radius, tiles, W, H)
+        idx_sorted, tile_range = _bin(uv_like, uv_stride, depth, radius, tiles, W, H, tight=tight)
         _CAPACITY[key] = int(idx_sorted.numel() * 1.25) + 65536
         return idx_sorted, tile_range, None
     n_tiles = ((W + TILE - 1) // TILE) * ((H + TILE - 1) // TILE)
@@ -259,12 +262,13 @@ def _bin_nosync(uv_like: Tensor, uv_stride: int, depth: Tensor, radius: Tensor, 
         idx_sorted = torch.empty(cap, dtype=torch.int32, device=dev)
         ws_n_bytes = lib.pxb_bin_sort_workspace_bytes(cap, int(W), int(H))
         ws_n = torch.empty(ws_n_bytes, dtype=torch.uint8, device=dev)
-        launch("pxb_sort_gaussian", P, cap, _p(total), _p(uv_like), uv_stride, _p(depth), _p(radius), _p(tiles), int(W),
+        launch("pxb_sort_gaussian", P, cap, _p(total), _p(uv_like), uv_stride, int(tight), _p(depth), _p(radius), _p(tiles), int(W),
                int(H), _p(idx_sorted), _p(tile_range), _p(None), _p(ws_p), ws_p_bytes, _p(ws_n), ws_n_bytes, stream)
 
     def check():
         ev.synchronize()
         n = int(n_host[0])
+        LAST_N[(dev.index, bool(tight))] = n
         if n > cap:
             _CAPACITY[key] = int(n * 1.25) + 65536
             return n

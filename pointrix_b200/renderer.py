@@ -81,13 +81,15 @@ class _FusedRender(torch.autograd.Function):
             stream = _stream(dev)
             launch("pxb_fused_forward", P, int(sh_degree), _p(pos), _p(sc), _p(rot), _p(op), _p(sh), _p(ex), n_extra,
                                         int(with_depth), _p(intr_c), _p(extr_c), _p(cc), W, H, float(nearest), 1.3, S,
-                                        _p(rec), _p(depth), _p(radius), _p(tiles), stream)
-            idx_sorted, tile_range, check = ops._bin_nosync(rec, S, depth, radius, tiles, W, H)
+                                        1, _p(rec), _p(depth), _p(radius), _p(tiles), stream)
+            # tight = 1: tile lists hold only the tiles the alpha >= 1/255 ellipse reaches (internal to
+            # the fused path; the msplat-level sort_gaussian op keeps the reference's lists)
+            idx_sorted, tile_range, check = ops._bin_nosync(rec, S, depth, radius, tiles, W, H, tight=True)
             launch("pxb_blend_forward", _p(rec), S, Cc, _p(idx_sorted), _p(tile_range), float(bg), W, H, _p(final_T),
                                         _p(ncontrib), _p(out), stream)
             if check is not None and check() is not None:
                 # more intersections than the learnt capacity: bin exactly and blend again
-                idx_sorted, tile_range = ops._bin(rec, S, depth, radius, tiles, W, H)
+                idx_sorted, tile_range = ops._bin(rec, S, depth, radius, tiles, W, H, tight=True)
                 launch("pxb_blend_forward", _p(rec), S, Cc, _p(idx_sorted), _p(tile_range), float(bg), W, H,
                        _p(final_T), _p(ncontrib), _p(out), stream)
         ctx.save_for_backward(pos, sc, rot, sh, intr_c, extr_c, cc, rec, depth, radius, idx_sorted, tile_range, final_T,
