@@ -190,6 +190,27 @@ def _main(out_f):
     r = pb.parse_renderer({"name": "MsplatRender"}, white_bg=True, device=str(dev))
     r.sh_degree = 3
 
+    # data-parallel exchange: the fused backward writes its gradients into symmetric memory and one
+    # hand-written kernel all-reduces them over NVLink (in-switch from 4 GPUs on); NCCL only if the
+    # group has no peer access
+    exch, exch_kind = None, "none"
+    if world > 1:
+        from pointrix_b200 import renderer as _renderer_mod
+
+        try:
+            exch = parallel.NvlsGradExchange(P, dev)
+            _renderer_mod.set_grad_sink(exch)
+            exch_kind = f"pxb_{exch.mode}_allreduce over symmetric memory"
+        except Exception as e:  # noqa: BLE001
+            exch, exch_kind = None, f"NCCL all-reduce ({type(e).__name__})"
+
+    def exchange(out, rw):
+        if exch is not None:
+            exch.exchange(out["radii"])
+        else:
+            parallel.allreduce_step([p_.grad for p_ in params.values()], out["uv_points"].grad, out["radii"], world,
+                                    average=False, radii_work=rw)
+
     def view_of(step):  # views sharded by rank
         return (step * world + rank) % V
 
@@ -198,13 +219,13 @@ def _main(out_f):
         for p_ in params.values():
             p_.grad = None
         out = r.render_iter(H, W, cam_src["extrinsic_matrix"][v], cam_src["intrinsic_params"], cam_src["camera_center"][v], **params)
-        rw = parallel.begin_radii_reduce(out["radii"], world)  # final after the forward: hides under the backward
+        # NCCL path only: radii are final after the forward, their reduce hides under the backward
+        rw = parallel.begin_radii_reduce(out["radii"], world) if exch is None else None
         img = out["rendered_features_split"]["rgb"]
         loss = (img * g_img).sum()
         loss.backward()
         if world > 1:
-            parallel.allreduce_step([p_.grad for p_ in params.values()], out["uv_points"].grad, out["radii"], world,
-                                    average=False, radii_work=rw)
+            exchange(out, rw)
         return loss, out
 
     def sync():
@@ -283,15 +304,14 @@ def _main(out_f):
         for p_ in params.values():
             p_.grad = None
         out = r.render_iter(H, W, E, I, Cc, **params)
-        rw = parallel.begin_radii_reduce(out["radii"], world)
+        rw = parallel.begin_radii_reduce(out["radii"], world) if exch is None else None
         img = out["rendered_features_split"]["rgb"]
         main.wait_stream(copy_stream)
         G.record_stream(main)
         loss = (img * G).sum()
         loss.backward()
         if world > 1:
-            parallel.allreduce_step([p_.grad for p_ in params.values()], out["uv_points"].grad, out["radii"], world,
-                                    average=False, radii_work=rw)
+            exchange(out, rw)
         res = torch.stack([loss.detach(), out["visibility"].sum().float()])
         res_host.copy_(res, non_blocking=True)
         main.synchronize()  # the caller consumes the result every step
@@ -382,7 +402,7 @@ def _main(out_f):
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_name(args.config), "intersections_reference_lists": N_ref,
                    "intersections_binned": N_mean,
-                   "parallelism": f"view-sharded dp{world}" + (", NCCL all-reduce of 59+2 floats/Gaussian + max(radii) per step" if world > 1 else ""),
+                   "parallelism": f"view-sharded dp{world}" + (f", all-reduce of 59+2 floats/Gaussian + max(radii) per step: {exch_kind}" if world > 1 else ""),
                    "cache": "inputs larger than L2 (236 MB Gaussian table + 48 MB records vs 126 MB L2); a different view every step"},
         "render_mpix_s": round(render_mpix, 2),
         "e2e": {"value": round(e2e_value, 3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},

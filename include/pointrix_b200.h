@@ -126,6 +126,20 @@ int pxb_fused_backward(int P, int sh_degree, const float* pos, const float* scal
                        const float* grec, float* d_pos, float* d_scales, float* d_quats, float* d_opacity,
                        float* d_shs, float* d_extra, float* d_ndc, float* d_cam, void* stream);
 
+/* ---- data-parallel gradient exchange (all-reduce(SUM) of the parameter gradients and
+ *      ndc.grad, all-reduce(MAX) of radii; the reference's equivalent is batch_size = world on one GPU,
+ *      pointrix/model/loss.py:27-46, pointrix/controller/gs.py:274-278, msplat.py:211-212).
+ *      In-switch (NVLS) all-reduce of a symmetric buffer [n_f32 floats | n_i32 int32] through its
+ *      multicast address mc_ptr: rank r reduces (float SUM, int MAX) and re-broadcasts its 1/world slice.
+ *      n_f32 % (4*world) == 0, n_i32 % world == 0.  The caller runs a cross-rank barrier before (all
+ *      replicas written) and after (all slices landed); the kernel itself never waits on a peer. ---- */
+int pxb_nvls_allreduce(void* mc_ptr, long long n_f32, long long n_i32, int rank, int world, void* stream);
+/* Same contract over plain peer mappings (peer_ptrs: HOST array of `world` device pointers, the replicas in
+ * rank order; world <= 16): rank r sums slice r over all replicas and stores it into every replica.
+ * Preferred for world = 2 and when the group has no multicast support. */
+int pxb_p2p_allreduce(const void* const* peer_ptrs, long long n_f32, long long n_i32, int rank, int world,
+                      void* stream);
+
 #ifdef __cplusplus
 }
 #endif

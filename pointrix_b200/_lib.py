@@ -40,6 +40,8 @@ SIGNATURES = {
     "pxb_blend_forward": (i32, [p, i32, i32, p, p, f32, i32, i32, p, p, p, p]),
     "pxb_blend_backward": (i32, [p, i32, i32, p, p, f32, i32, i32, p, p, p, p, p]),
     "pxb_fused_forward": (i32, [i32, i32, p, p, p, p, p, p, i32, i32, p, p, p, i32, i32, f32, f32, i32, i32, p, p, p, p, p]),
+    "pxb_nvls_allreduce": (i32, [p, i64, i64, i32, i32, p]),
+    "pxb_p2p_allreduce": (i32, [p, i64, i64, i32, i32, p]),
     "pxb_fused_backward": (i32, [i32, i32, p, p, p, p, i32, i32, p, p, p, i32, i32, i32, p, p, p, p, p, p, p, p, p, p, p, p]),
 }
 

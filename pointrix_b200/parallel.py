@@ -76,3 +76,87 @@ def allreduce_step(param_grads: Sequence[torch.Tensor], ndc_grad: Optional[torch
     for w in works:
         w.wait()
     return radii > 0
+
+
+class NvlsGradExchange:
+    """Per-step exchange of the fused render path over NVLink 5 / NVSwitch without NCCL on the data path.
+
+    The fused backward writes every P-sized gradient (59 parameter floats + 2 ndc floats per Gaussian)
+    straight into a *symmetric* buffer (``torch.distributed._symmetric_memory``: same allocation on
+    every rank, mapped into all peers and into one multicast address); :meth:`exchange` then runs
+    ``pxb_nvls_allreduce`` -- each rank pulls its 1/world slice reduced inside the switch
+    (``multimem.ld_reduce``: SUM for the gradients, MAX for radii) and multicasts the result back
+    (``multimem.st``) -- between two cross-rank barriers.  Afterwards the ``.grad`` tensors the backward
+    handed to autograd (views of the buffer) and ``radii`` hold the batch values on every rank.
+
+    Semantics are those of :func:`allreduce_step` with ``average=False``: the caller's loss carries the
+    1/world factor.  ``nbuf`` buffers rotate, so the gradients of step k stay valid until the backward
+    of step k + nbuf (an optimizer consumes them long before).  Use once per backward.
+    """
+
+    def __init__(self, P: int, device, group=None, nbuf: int = 2, mode: str = "auto"):
+        import ctypes as C
+
+        import torch.distributed._symmetric_memory as symm
+
+        from . import _lib
+
+        self._C, self._lib = C, _lib
+        self.group = group if group is not None else dist.group.WORLD
+        self.world = dist.get_world_size(self.group)
+        self.rank = dist.get_rank(self.group)
+        self.P = int(P)
+        self.device = torch.device(device)
+        q = 4 * self.world
+        self.n_f32 = (61 * self.P + q - 1) // q * q
+        self.n_i32 = (self.P + q - 1) // q * q
+        self.bufs, self.hdls = [], []
+        for _ in range(nbuf):
+            t = symm.empty(self.n_f32 + self.n_i32, dtype=torch.float32, device=self.device)
+            h = symm.rendezvous(t, self.group.group_name)
+            t.zero_()
+            self.bufs.append(t)
+            self.hdls.append(h)
+        # multicast (in-switch reduction) moves (1 + 1/n) buffer sizes per GPU and direction, plain peer
+        # loads/stores 2(n-1)/n: peer-to-peer wins for two GPUs, the switch from four on
+        has_mc = all(bool(h.has_multicast_support) and bool(h.multicast_ptr) for h in self.hdls)
+        if mode == "auto":
+            mode = "nvls" if (has_mc and self.world > 2) else "p2p"
+        if mode == "nvls" and not has_mc:
+            raise RuntimeError("NVLS multicast is not available for this group")
+        self.mode = mode
+        self._peer_arrays = [(C.c_void_p * self.world)(*[int(x) for x in h.buffer_ptrs]) for h in self.hdls]
+        self._next = 0
+        self._cur = None
+        torch.cuda.synchronize(self.device)
+        dist.barrier(self.group)
+
+    # called by the fused backward: where the flat gradient buffer of this step lives
+    def next_buffer(self, numel: int) -> Optional[torch.Tensor]:
+        if numel != 61 * self.P:
+            return None
+        self._cur = self._next
+        self._next = (self._next + 1) % len(self.bufs)
+        return self.bufs[self._cur][:numel]
+
+    def exchange(self, radii: torch.Tensor) -> torch.Tensor:
+        """All-reduce the gradients written by the last backward (SUM) and ``radii`` (MAX, in place);
+        returns the batch visibility."""
+        if self._cur is None:
+            raise RuntimeError("no backward has written into the exchange buffer since the last exchange")
+        buf, h = self.bufs[self._cur], self.hdls[self._cur]
+        self._last = self._cur
+        self._cur = None
+        ri = buf[self.n_f32:].view(torch.int32)
+        ri[: self.P].copy_(radii.reshape(-1))
+        stream = torch.cuda.current_stream(self.device)
+        h.barrier(channel=0)  # every rank's replica is written
+        if self.mode == "nvls":
+            self._lib.launch("pxb_nvls_allreduce", self._C.c_void_p(h.multicast_ptr), self.n_f32, self.n_i32, self.rank,
+                             self.world, self._C.c_void_p(stream.cuda_stream))
+        else:
+            self._lib.launch("pxb_p2p_allreduce", self._peer_arrays[self._last], self.n_f32, self.n_i32, self.rank,
+                             self.world, self._C.c_void_p(stream.cuda_stream))
+        h.barrier(channel=1)  # every slice has been multicast back
+        radii.reshape(-1).copy_(ri[: self.P])
+        return radii > 0

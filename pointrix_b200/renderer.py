@@ -54,6 +54,18 @@ class RenderFeatures:
         return out
 
 
+# Optional owner of the flat gradient buffer (parallel.NvlsGradExchange: symmetric memory, so the
+# data-parallel exchange reduces the gradients in place over NVLink without a staging copy).
+_GRAD_SINK = None
+
+
+def set_grad_sink(sink) -> None:
+    """``sink.next_buffer(numel) -> Tensor | None`` supplies the buffer the fused backward writes the
+    P-sized gradients into (None: allocate).  Pass None to detach."""
+    global _GRAD_SINK
+    _GRAD_SINK = sink
+
+
 class _FusedRender(torch.autograd.Function):
     """render_iter's differentiable core: (Gaussians, camera) -> blended features."""
 
@@ -109,7 +121,9 @@ class _FusedRender(torch.autograd.Function):
         grec = torch.zeros(max(P, 1), S, dtype=torch.float32, device=dev)
         # every P-sized gradient lives in ONE flat buffer (the 16-byte-aligned blocks first), so a
         # data-parallel caller exchanges them with a single collective (parallel.allreduce_step)
-        flat = torch.empty(61 * P, dtype=torch.float32, device=dev)
+        flat = _GRAD_SINK.next_buffer(61 * P) if _GRAD_SINK is not None else None
+        if flat is None or flat.device != dev:
+            flat = torch.empty(61 * P, dtype=torch.float32, device=dev)
         d_sh = flat[0:48 * P].view(P, 16, 3)
         d_rot = flat[48 * P:52 * P].view(P, 4)
         d_pos = flat[52 * P:55 * P].view(P, 3)
