@@ -381,8 +381,12 @@ def _main(out_f):
             stages[name].update({"alg_bytes": int(b), "achieved_gbs": round(gbs, 1), "frac_of_hbm_peak": round(gbs / hbm_peak, 4)})
     dom = max(kern.items(), key=lambda kv: kv[1]["ms_total"])[0]
     dom_gbs = alg[dom] / (kern[dom]["ms_avg"] * 1e-3) / 1e9
+    traffic = None  # DRAM bytes per launch of that kernel from the committed ncu --set full capture
+    tj = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if args.config == "cfg4" and os.path.exists(tj):
+        traffic = json.load(open(tj)).get(dom, {}).get("dram_bytes_per_launch")
     roofline = {"kernel": dom, "bound": "hbm", "achieved": round(dom_gbs, 1), "peak": hbm_peak, "unit": "GB/s",
-                "frac": round(dom_gbs / hbm_peak, 4), "traffic": None, "peak_source": peak_src,
+                "frac": round(dom_gbs / hbm_peak, 4), "traffic": traffic, "peak_source": peak_src,
                 "note": "blend kernels are FP32-issue/shared-memory bound, not HBM bound: see blend_issue_roofline"}
     # blending as (pixel,Gaussian) pair tests against the FP32 issue bound
     sm_clk = (clocks or {}).get("sm_mhz") or 1965.0
