@@ -126,6 +126,34 @@ int pxb_fused_backward(int P, int sh_degree, const float* pos, const float* scal
                        const float* grec, float* d_pos, float* d_scales, float* d_quats, float* d_opacity,
                        float* d_shs, float* d_extra, float* d_ndc, float* d_cam, void* stream);
 
+/* ---- one view of MsplatRender.render_iter behind ONE call each way
+ *      (pointrix/model/renderer/msplat.py:94-151 and its autograd graph): pxb_fused_forward (tight
+ *      tile counts) -> pxb_bin_prepare -> pxb_sort_gaussian (capacity mode) -> pxb_blend_forward, queued
+ *      back to back on `stream`.  N_cap: intersection capacity idx_sorted[N_cap] and the workspace are
+ *      sized for.  total_host: pinned, device-accessible host int; the caller stores -1 before the
+ *      call and reads it after the call returns (spinning while it is -1): a value > N_cap means the
+ *      lists were truncated and the call must be repeated with a larger capacity, otherwise the
+ *      outputs are exact.  stage_events: NULL, or 5 cudaEvent_t recorded before the first and after each
+ *      of the four stages (per-stage timing).  ws: pxb_render_workspace_bytes(P, N_cap, W, H) bytes,
+ *      256-byte aligned, scratch (nothing in it is needed by the backward).
+ *      Saved for the backward: rec[P,S], depth[P], radius[P], idx_sorted, tile_range, final_T, ncontrib. ---- */
+size_t pxb_render_workspace_bytes(int P, long long N_cap, int W, int H);
+int pxb_render_forward(int P, int sh_degree, const float* pos, const float* scales, const float* quats,
+                       const float* opacity, const float* shs, const float* extra, int n_extra, int with_depth,
+                       const float* intr, const float* extr, const float* cam_center, int W, int H, float nearest,
+                       float extent, float bg, int S, long long N_cap, float* rec, float* depth, int* radius,
+                       int* idx_sorted, int* tile_range, float* final_T, int* ncontrib, float* out, int* total_host,
+                       void* ws, size_t ws_bytes, void* const* stage_events, void* stream);
+/* grec[P,S]: scratch (zeroed inside); d_cam[19] or NULL (zeroed inside); stage_events: NULL or 3 events
+ * (before blend backward, between, after the per-Gaussian backward). */
+int pxb_render_backward(int P, int sh_degree, const float* pos, const float* scales, const float* quats,
+                        const float* shs, int n_extra, int with_depth, const float* intr, const float* extr,
+                        const float* cam_center, int W, int H, float bg, int S, const float* rec, const float* depth,
+                        const int* radius, const int* idx_sorted, const int* tile_range, const float* final_T,
+                        const int* ncontrib, const float* dL_dout, float* grec, float* d_pos, float* d_scales,
+                        float* d_quats, float* d_opacity, float* d_shs, float* d_extra, float* d_ndc, float* d_cam,
+                        void* const* stage_events, void* stream);
+
 /* ---- data-parallel gradient exchange (all-reduce(SUM) of the parameter gradients and
  *      ndc.grad, all-reduce(MAX) of radii; the reference's equivalent is batch_size = world on one GPU,
  *      pointrix/model/loss.py:27-46, pointrix/controller/gs.py:274-278, msplat.py:211-212).

@@ -40,6 +40,11 @@ SIGNATURES = {
     "pxb_blend_forward": (i32, [p, i32, i32, p, p, f32, i32, i32, p, p, p, p]),
     "pxb_blend_backward": (i32, [p, i32, i32, p, p, f32, i32, i32, p, p, p, p, p]),
     "pxb_fused_forward": (i32, [i32, i32, p, p, p, p, p, p, i32, i32, p, p, p, i32, i32, f32, f32, i32, i32, p, p, p, p, p]),
+    "pxb_render_workspace_bytes": (sz, [i32, i64, i32, i32]),
+    "pxb_render_forward": (i32, [i32, i32, p, p, p, p, p, p, i32, i32, p, p, p, i32, i32, f32, f32, f32, i32, i64,
+                                 p, p, p, p, p, p, p, p, p, p, sz, p, p]),
+    "pxb_render_backward": (i32, [i32, i32, p, p, p, p, i32, i32, p, p, p, i32, i32, f32, i32, p, p, p, p, p, p, p,
+                                  p, p, p, p, p, p, p, p, p, p, p, p]),
     "pxb_nvls_allreduce": (i32, [p, i64, i64, i32, i32, p]),
     "pxb_p2p_allreduce": (i32, [p, i64, i64, i32, i32, p]),
     "pxb_fused_backward": (i32, [i32, i32, p, p, p, p, i32, i32, p, p, p, i32, i32, i32, p, p, p, p, p, p, p, p, p, p, p, p]),
@@ -115,14 +120,26 @@ def set_timer(t):
     _timer = t
 
 
+def _sort_kernels(W: int, H: int) -> int:
+    nt = ((W + 15) // 16) * ((H + 15) // 16)
+    return 2 + 3 * max(1, (max(nt - 1, 0).bit_length() + 7) // 8)
+
+
+def count_launches(name: str, W: int, H: int) -> None:
+    """Launch accounting of the whole-view entry points (called by the renderer)."""
+    global launch_count
+    n = (1 + KERNELS_PER_CALL["pxb_bin_prepare"] + _sort_kernels(W, H) + 1) if name == "pxb_render_forward" else 2
+    launch_count += n
+    if _timer is not None:
+        _timer.launches += n
+
+
 def launch(name: str, *args) -> None:
     global launch_count
     fn = getattr(lib, name)
     n = KERNELS_PER_CALL.get(name, 1)
     if name == "pxb_sort_gaussian":
-        W, H = args[9], args[10]
-        nt = ((W + 15) // 16) * ((H + 15) // 16)
-        n = (2 + 3 * max(1, (max(nt - 1, 0).bit_length() + 7) // 8)) if args[1] > 0 else 0
+        n = _sort_kernels(args[9], args[10]) if args[1] > 0 else 0
     launch_count += n
     if _timer is None:
         check(fn(*args), name)

@@ -31,7 +31,8 @@ constexpr int kScanTile = kScanThreads * kScanItems;
 // out[i] = sum_{j<=i} cnt(order[j]),  cnt(g) = radius[g] > 0 ? tiles[g] : 0
 __global__ void __launch_bounds__(kScanThreads)
 scan_kernel(int P, const int* __restrict__ tiles, const int* __restrict__ radius, const unsigned int* __restrict__ order,
-            int* __restrict__ out, int* __restrict__ total, unsigned long long* status, unsigned int* ticket) {
+            int* __restrict__ out, int* __restrict__ total, int* __restrict__ total_host, unsigned long long* status,
+            unsigned int* ticket) {
     __shared__ int s_warp[kScanThreads / 32];
     __shared__ int s_tile, s_excl;
     if (threadIdx.x == 0) s_tile = (int)atomicAdd(ticket, 1u);
@@ -90,7 +91,13 @@ scan_kernel(int P, const int* __restrict__ tiles, const int* __restrict__ radius
         if (lane == 0) {
             if (tile > 0) st[tile] = kFlagPrefix | (unsigned int)(excl + block_sum);
             s_excl = excl;
-            if ((tile + 1) * kScanTile >= P) *total = excl + block_sum;
+            if ((tile + 1) * kScanTile >= P) {
+                *total = excl + block_sum;
+                if (total_host) {  // pinned host word the caller polls (no memcpy in the stream)
+                    *reinterpret_cast<volatile int*>(total_host) = excl + block_sum;
+                    __threadfence_system();
+                }
+            }
         }
     }
     __syncthreads();
@@ -572,6 +579,14 @@ size_t pxb_bin_sort_workspace_bytes(long long N_cap, int W, int H) {
 // *total_dev = number of intersections N.  ws_p must stay untouched until pxb_sort_gaussian.
 int pxb_bin_prepare(int P, const float* depth, const int* radius, const int* tiles, int* total_dev, void* ws_p,
                     size_t ws_p_bytes, void* stream) {
+    return pxb::bin_prepare(P, depth, radius, tiles, total_dev, nullptr, ws_p, ws_p_bytes, stream);
+}
+
+}  // extern "C"
+
+// total_host: optional pinned (device-mapped) host word that also receives the count
+int pxb::bin_prepare(int P, const float* depth, const int* radius, const int* tiles, int* total_dev, int* total_host,
+                     void* ws_p, size_t ws_p_bytes, void* stream) {
     cudaStream_t s = (cudaStream_t)stream;
     if (P <= 0) return (int)cudaMemsetAsync(total_dev, 0, sizeof(int), s);
     WsP b = carve_p(ws_p, P);
@@ -581,9 +596,11 @@ int pxb_bin_prepare(int P, const float* depth, const int* radius, const int* til
     int rc = radix_sort_u32(b.keys, b.vals, P, nullptr, 32, b.counts, b.totals, s);  // -> keys[0]/vals[0]
     if (rc) return rc;
     scan_kernel<<<(P + kScanTile - 1) / kScanTile, kScanThreads, 0, s>>>(P, tiles, radius, b.vals[0], b.offsets, total_dev,
-                                                                        b.scan_status, b.scan_ticket);
+                                                                        total_host, b.scan_status, b.scan_ticket);
     return (int)cudaGetLastError();
 }
+
+extern "C" {
 
 // keys + tile sort + ranges.  N: exact count when total_dev == NULL, else a capacity: the kernels
 // then process min(*total_dev, N) intersections and the caller verifies *total_dev <= N afterwards.

@@ -251,4 +251,9 @@ __device__ __forceinline__ unsigned lane_id() { return threadIdx.x & 31u; }
         if (_e != cudaSuccess) return (int)_e; \
     } while (0)
 
+// library-internal (not part of the C ABI): pxb_bin_prepare with an optional pinned, device-mapped host
+// word that also receives the intersection count (binning.cu)
+int bin_prepare(int P, const float* depth, const int* radius, const int* tiles, int* total_dev, int* total_host,
+                void* ws_p, size_t ws_p_bytes, void* stream);
+
 }  // namespace pxb

@@ -225,58 +225,7 @@ def _bin(uv_like: Tensor, uv_stride: int, depth: Tensor, radius: Tensor, tiles: 
     return idx_sorted, tile_range
 
 
-# capacity of the sync-free binning per (device, P, W, H): learnt from the previous views
-_CAPACITY = {}
-_PINNED = {}
 LAST_N = {}  # (device index, tight) -> intersection count of the most recent binning (diagnostics / bench)
-
-
-def _bin_nosync(uv_like: Tensor, uv_stride: int, depth: Tensor, radius: Tensor, tiles: Tensor, W: int, H: int,
-                tight: bool = False):
-    """Binning without a host round trip on the critical path (fused plugin path).
-
-    Buffers and grids are sized for a capacity learnt from earlier views; the kernels read the
-    actual intersection count on the device.  Returns ``(idx_sorted[cap], tile_range, check)``
-    where ``check()`` -- to be called once the rest of the forward has been queued -- waits for the
-    count (copied to pinned memory right after the prepare step), and returns None if it fitted or
-    the exact count if the capacity was exceeded (the caller then re-bins and re-blends; rare)."""
-    dev = depth.device
-    P = radius.numel()
-    key = (dev.index, P, int(W), int(H), bool(tight))
-    cap = _CAPACITY.get(key)
-    if cap is None or P == 0:
-        idx_sorted, tile_range = _bin(uv_like, uv_stride, depth, radius, tiles, W, H, tight=tight)
-        _CAPACITY[key] = int(idx_sorted.numel() * 1.25) + 65536
-        return idx_sorted, tile_range, None
-    n_tiles = ((W + TILE - 1) // TILE) * ((H + TILE - 1) // TILE)
-    tile_range = torch.empty(n_tiles, 2, dtype=torch.int32, device=dev)
-    with torch.cuda.device(dev):
-        stream = _stream(dev)
-        total, ws_p, ws_p_bytes = _prepare(depth, radius, tiles, stream)
-        n_host = _PINNED.get(dev.index)
-        if n_host is None:
-            n_host = _PINNED[dev.index] = torch.zeros(1, dtype=torch.int32).pin_memory()
-        n_host.copy_(total, non_blocking=True)
-        ev = torch.cuda.Event()
-        ev.record()
-        idx_sorted = torch.empty(cap, dtype=torch.int32, device=dev)
-        ws_n_bytes = lib.pxb_bin_sort_workspace_bytes(cap, int(W), int(H))
-        ws_n = torch.empty(ws_n_bytes, dtype=torch.uint8, device=dev)
-        launch("pxb_sort_gaussian", P, cap, _p(total), _p(uv_like), uv_stride, int(tight), _p(depth), _p(radius), _p(tiles), int(W),
-               int(H), _p(idx_sorted), _p(tile_range), _p(None), _p(ws_p), ws_p_bytes, _p(ws_n), ws_n_bytes, stream)
-
-    def check():
-        ev.synchronize()
-        n = int(n_host[0])
-        LAST_N[(dev.index, bool(tight))] = n
-        if n > cap:
-            _CAPACITY[key] = int(n * 1.25) + 65536
-            return n
-        if n * 2 < cap:  # shrink slowly when the scene got much lighter
-            _CAPACITY[key] = max(int(n * 1.25) + 65536, int(cap * 0.9))
-        return None
-
-    return idx_sorted, tile_range, check
 
 
 def sort_gaussian(uv: Tensor, depth: Tensor, W: int, H: int, radius: Tensor, tiles: Tensor, return_keys: bool = False):

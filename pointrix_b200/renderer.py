@@ -14,14 +14,15 @@ reference's ~14 kernels + ~40 torch ops; the autograd graph of ``render_iter``
 from __future__ import annotations
 
 import ctypes as C
+import time
 from dataclasses import dataclass
 from typing import Dict, Optional
 
 import torch
 from torch import Tensor
 
-from . import ops
-from ._lib import launch, lib
+from . import _lib, ops
+from ._lib import lib
 from .ops import _f32, _p, _stream
 from .registry import BaseObject, register_renderer
 
@@ -66,8 +67,51 @@ def set_grad_sink(sink) -> None:
     _GRAD_SINK = sink
 
 
+# per-device pinned word the forward's scan kernel stores the intersection count into, scratch
+# workspaces per (device, stream, P, capacity, W, H), and the learnt intersection capacity
+_COUNT_WORD = {}
+_WORKSPACE = {}
+_CAPACITY = {}
+_raw_stream = torch._C._cuda_getCurrentRawStream
+
+
+def _count_word(dev_index: int):
+    w = _COUNT_WORD.get(dev_index)
+    if w is None:
+        t = torch.zeros(16, dtype=torch.int32).pin_memory()
+        w = _COUNT_WORD[dev_index] = (t, C.c_int.from_address(t.data_ptr()))
+    return w
+
+
+def _wait_count(word) -> int:
+    """Spin until the device has stored the count (it does so ~0.2 ms after the call, while the
+    blend kernel is queued behind it)."""
+    n = word.value
+    if n != -1:
+        return n
+    deadline = time.monotonic() + 30.0
+    while True:
+        for _ in range(4096):
+            n = word.value
+            if n != -1:
+                return n
+        if time.monotonic() > deadline:
+            torch.cuda.synchronize()  # surfaces a launch failure as a CUDA error
+            if word.value == -1:
+                raise RuntimeError("pointrix_b200: the binning kernels never reported an intersection count")
+
+
+def _stage_events(n: int):
+    """n timing events with live handles (torch creates the CUDA event on the first record)."""
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(n)]
+    for e in evs:
+        e.record()
+    return evs, (C.c_void_p * n)(*[e.cuda_event for e in evs])
+
+
 class _FusedRender(torch.autograd.Function):
-    """render_iter's differentiable core: (Gaussians, camera) -> blended features."""
+    """render_iter's differentiable core: (Gaussians, camera) -> blended features.
+    One foreign call forward (pxb_render_forward), one backward (pxb_render_backward)."""
 
     @staticmethod
     def forward(ctx, position, opacity, scaling, rotation, shs, extra, intr, extr, cam_center, ndc, sh_degree, W, H,
@@ -82,28 +126,56 @@ class _FusedRender(torch.autograd.Function):
         Cc = 3 + int(with_depth) + n_extra
         S = lib.pxb_record_stride(Cc)
         W, H = int(W), int(H)
-        rec = torch.empty(max(P, 1), S, dtype=torch.float32, device=dev)
-        depth = torch.empty(max(P, 1), dtype=torch.float32, device=dev)
-        radius = torch.empty(P, dtype=torch.int32, device=dev)
-        tiles = torch.empty(max(P, 1), dtype=torch.int32, device=dev)
-        out = torch.empty(Cc, H, W, dtype=torch.float32, device=dev)
-        final_T = torch.empty(H, W, dtype=torch.float32, device=dev)
-        ncontrib = torch.empty(H, W, dtype=torch.int32, device=dev)
-        with torch.cuda.device(dev):
-            stream = _stream(dev)
-            launch("pxb_fused_forward", P, int(sh_degree), _p(pos), _p(sc), _p(rot), _p(op), _p(sh), _p(ex), n_extra,
-                                        int(with_depth), _p(intr_c), _p(extr_c), _p(cc), W, H, float(nearest), 1.3, S,
-                                        1, _p(rec), _p(depth), _p(radius), _p(tiles), stream)
-            # tight = 1: tile lists hold only the tiles the alpha >= 1/255 ellipse reaches (internal to
-            # the fused path; the msplat-level sort_gaussian op keeps the reference's lists)
-            idx_sorted, tile_range, check = ops._bin_nosync(rec, S, depth, radius, tiles, W, H, tight=True)
-            launch("pxb_blend_forward", _p(rec), S, Cc, _p(idx_sorted), _p(tile_range), float(bg), W, H, _p(final_T),
-                                        _p(ncontrib), _p(out), stream)
-            if check is not None and check() is not None:
-                # more intersections than the learnt capacity: bin exactly and blend again
-                idx_sorted, tile_range = ops._bin(rec, S, depth, radius, tiles, W, H, tight=True)
-                launch("pxb_blend_forward", _p(rec), S, Cc, _p(idx_sorted), _p(tile_range), float(bg), W, H,
-                       _p(final_T), _p(ncontrib), _p(out), stream)
+        n_tiles = ((W + 15) // 16) * ((H + 15) // 16)
+        E = torch.empty
+        f32, i32 = torch.float32, torch.int32
+        rec = E((P, S), dtype=f32, device=dev)
+        depth = E((P,), dtype=f32, device=dev)
+        radius = E((P,), dtype=i32, device=dev)
+        tile_range = E((n_tiles, 2), dtype=i32, device=dev)
+        out = E((Cc, H, W), dtype=f32, device=dev)
+        final_T = E((H, W), dtype=f32, device=dev)
+        ncontrib = E((H, W), dtype=i32, device=dev)
+        _lib.ensure_init()
+        host_t, word = _count_word(dev.index)
+        ckey = (dev.index, P, W, H)
+        cap = _CAPACITY.get(ckey) or max(4 * P, 1 << 20)
+        timer = _lib._timer
+        same_dev = torch.cuda.current_device() == dev.index
+        while True:
+            stream = _raw_stream(dev.index)
+            wkey = (dev.index, stream, P, cap, W, H)
+            ws = _WORKSPACE.get(wkey)
+            if ws is None:
+                for k in [k for k in _WORKSPACE if k[:2] == wkey[:2]]:
+                    del _WORKSPACE[k]  # one live workspace per (device, stream)
+                ws = _WORKSPACE[wkey] = E((lib.pxb_render_workspace_bytes(P, cap, W, H),), dtype=torch.uint8, device=dev)
+            idx_sorted = E((cap,), dtype=i32, device=dev)
+            evs, ev_arr = _stage_events(5) if timer is not None else (None, None)
+            word.value = -1
+            args = (P, int(sh_degree), _p(pos), _p(sc), _p(rot), _p(op), _p(sh), _p(ex), n_extra, int(with_depth),
+                    _p(intr_c), _p(extr_c), _p(cc), W, H, float(nearest), 1.3, float(bg), S, cap, _p(rec), _p(depth),
+                    _p(radius), _p(idx_sorted), _p(tile_range), _p(final_T), _p(ncontrib), _p(out),
+                    host_t.data_ptr(), _p(ws), ws.numel(), ev_arr, stream)
+            if same_dev:
+                _lib.check(lib.pxb_render_forward(*args), "pxb_render_forward")
+            else:
+                with torch.cuda.device(dev):
+                    _lib.check(lib.pxb_render_forward(*args), "pxb_render_forward")
+            _lib.count_launches("pxb_render_forward", W, H)
+            n = _wait_count(word)
+            ops.LAST_N[(dev.index, True)] = n
+            if timer is not None:
+                for k, name in enumerate(("pxb_fused_forward", "pxb_bin_prepare", "pxb_sort_gaussian", "pxb_blend_forward")):
+                    timer.events.append((name, evs[k], evs[k + 1]))
+            if n <= cap:
+                if 2 * n < cap:  # shrink slowly when the scene got much lighter
+                    _CAPACITY[ckey] = max(int(n * 1.25) + 65536, int(cap * 0.9))
+                else:
+                    _CAPACITY[ckey] = cap
+                break
+            # more intersections than the capacity: the lists were truncated, run again with room
+            cap = _CAPACITY[ckey] = int(n * 1.25) + 65536
         ctx.save_for_backward(pos, sc, rot, sh, intr_c, extr_c, cc, rec, depth, radius, idx_sorted, tile_range, final_T,
                               ncontrib)
         ctx.meta = (int(sh_degree), W, H, float(bg), int(with_depth), n_extra, S, Cc,
@@ -118,7 +190,7 @@ class _FusedRender(torch.autograd.Function):
         dev = pos.device
         P = pos.shape[0]
         g = _f32(d_out, "dL_drendered")
-        grec = torch.zeros(max(P, 1), S, dtype=torch.float32, device=dev)
+        grec = torch.empty((P, S), dtype=torch.float32, device=dev)  # zeroed by the call
         # every P-sized gradient lives in ONE flat buffer (the 16-byte-aligned blocks first), so a
         # data-parallel caller exchanges them with a single collective (parallel.allreduce_step)
         flat = _GRAD_SINK.next_buffer(61 * P) if _GRAD_SINK is not None else None
@@ -132,14 +204,20 @@ class _FusedRender(torch.autograd.Function):
         d_ndc = flat[59 * P:61 * P].view(P, 2)
         d_extra = torch.empty(P, n_extra, dtype=torch.float32, device=dev) if n_extra > 0 else None
         need_cam = any(ctx.needs_input_grad[6:9])
-        d_cam = torch.zeros(19, dtype=torch.float32, device=dev) if need_cam else None
+        d_cam = torch.empty(19, dtype=torch.float32, device=dev) if need_cam else None
+        timer = _lib._timer
+        base = flat.data_ptr()
         with torch.cuda.device(dev):
-            stream = _stream(dev)
-            launch("pxb_blend_backward", _p(rec), S, Cc, _p(idx_sorted), _p(tile_range), bg, W, H, _p(final_T),
-                                         _p(ncontrib), _p(g), _p(grec), stream)
-            launch("pxb_fused_backward", P, sh_degree, _p(pos), _p(sc), _p(rot), _p(sh), n_extra, with_depth, _p(intr),
-                                         _p(extr), _p(cc), W, H, S, _p(depth), _p(radius), _p(grec), _p(d_pos), _p(d_sc),
-                                         _p(d_rot), _p(d_op), _p(d_sh), _p(d_extra), _p(d_ndc), _p(d_cam), stream)
+            evs, ev_arr = _stage_events(3) if timer is not None else (None, None)
+            _lib.check(lib.pxb_render_backward(
+                P, sh_degree, _p(pos), _p(sc), _p(rot), _p(sh), n_extra, with_depth, _p(intr), _p(extr), _p(cc), W, H, bg,
+                S, _p(rec), _p(depth), _p(radius), _p(idx_sorted), _p(tile_range), _p(final_T), _p(ncontrib), _p(g),
+                _p(grec), base + 4 * 52 * P, base + 4 * 55 * P, base + 4 * 48 * P, base + 4 * 58 * P, base,
+                _p(d_extra), base + 4 * 59 * P, _p(d_cam), ev_arr, _raw_stream(dev.index)), "pxb_render_backward")
+        _lib.count_launches("pxb_render_backward", W, H)
+        if timer is not None:
+            timer.events.append(("pxb_blend_backward", evs[0], evs[1]))
+            timer.events.append(("pxb_fused_backward", evs[1], evs[2]))
         d_intr = d_cam[0:4].reshape(s_intr) if ctx.needs_input_grad[6] else None
         d_extr = d_cam[4:16].reshape(s_extr) if ctx.needs_input_grad[7] else None
         d_cc = d_cam[16:19].reshape(s_cc) if ctx.needs_input_grad[8] else None
@@ -204,9 +282,12 @@ class MsplatRender(BaseObject):
                                                   rotation, shs, extra, ndc)
         split, s = {}, 0
         names = [("rgb", 3)] + ([("depth", 1)] if self.cfg.render_depth else []) + [(k, v.shape[1]) for k, v in extras.items()]
-        for k, c in names:
-            split[k] = feats[s:s + c]
-            s += c
+        if len(names) == 1:  # rgb only: hand out the buffer itself (a slice costs a zeros+copy in autograd)
+            split["rgb"] = feats
+        else:
+            for k, c in names:
+                split[k] = feats[s:s + c]
+                s += c
         return {"rendered_features_split": split, "uv_points": ndc, "visibility": radius > 0, "radii": radius}
 
     def _render_iter_ops(self, height, width, extr, intr, camera_center, position, opacity, scaling, rotation, shs,
