@@ -172,6 +172,7 @@ def _main(out_f):
     ap.add_argument("--cpu-sample", type=int, default=100_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ref-gpu", action="store_true")
+    ap.add_argument("--no-loss-leg", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args, out_f)
@@ -348,6 +349,8 @@ def _main(out_f):
             dist.destroy_process_group()
         return
 
+    loss_info = photometric_loss_leg(r, params, cams_d, view_of, H, W, K, dev) if world == 1 and not args.no_loss_leg else None
+
     # ---- roofline bookkeeping (algorithmic bytes per SURVEY.md 8d / DESIGN.md) -----------
     peaks = {}
     pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -425,6 +428,8 @@ def _main(out_f):
         "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "roofline_stages": stages,
         "blend_issue_roofline": blend_issue,
     }
+    if loss_info is not None:
+        line["photometric_loss"] = loss_info
     if not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_oracle_run(args.config, args.cpu_sample, 2, 1)
     if world == 1 and not args.no_ref_gpu:
@@ -433,6 +438,57 @@ def _main(out_f):
     out_f.flush()
     if world > 1:
         dist.destroy_process_group()
+
+
+def photometric_loss_leg(r, params, cams_d, view_of, H, W, K, dev):
+    """SURVEY.md 8f row f1 beside the path: the fused (1-l)*L1 + l*(1-SSIM) loss (csrc/loss.cu) timed alone
+    (fwd+bwd, CUDA events, 8 rotating image pairs = 400 MB > L2), the same loss written with the reference's
+    torch ops on the same GPU (oracle/loss_oracle.py = pointrix/model/loss.py's formulation: 5 cuDNN depthwise
+    convolutions + elementwise kernels + autograd), and the training step render -> loss -> backward."""
+    import torch
+
+    from oracle import loss_oracle as LO
+    from pointrix_b200 import loss as PL
+
+    g = torch.Generator(device=dev).manual_seed(2)
+    gts = [torch.rand(1, 3, H, W, device=dev, generator=g) for _ in range(8)]
+    preds = [(t + 0.1 * torch.randn(t.shape, device=dev, generator=g)).clamp(0, 1) for t in gts]
+
+    def timed(fn, n):
+        for i in range(3):
+            fn(i)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(n):
+            fn(i)
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n
+
+    def ours(i):
+        p = preds[i % 8].detach().requires_grad_()
+        PL.l1_ssim_loss(p, gts[i % 8], 0.2)["loss"].backward()
+
+    def torch_ops(i):
+        p = preds[i % 8].detach().requires_grad_()
+        LO.l1_ssim_loss(p, gts[i % 8], 0.2)["loss"].backward()
+
+    def train_step(i):
+        v = view_of(i)
+        for p_ in params.values():
+            p_.grad = None
+        out = r.render_iter(H, W, cams_d["extrinsic_matrix"][v], cams_d["intrinsic_params"], cams_d["camera_center"][v], **params)
+        PL.l1_ssim_loss(out["rendered_features_split"]["rgb"].unsqueeze(0), gts[i % 8], 0.2)["loss"].backward()
+
+    n = max(10, min(K, 50))
+    ms_ours, ms_ref, ms_step = timed(ours, n), timed(torch_ops, n), timed(train_step, n)
+    px = 3 * H * W
+    alg = px * (8 + 12) + px * (20 + 4)  # forward 8 read + 12 written, backward 20 read + 4 written per pixel-channel
+    return {"fused_fwd_bwd_ms": round(ms_ours, 4), "torch_ops_fwd_bwd_ms": round(ms_ref, 4),
+            "alg_bytes": alg, "achieved_gbs": round(alg / (ms_ours * 1e-3) / 1e9, 1),
+            "train_step_render_loss_bwd_it_s": round(1e3 / ms_step, 2), "train_step_ms": round(ms_step, 4),
+            "note": "loss = 0.8*L1 + 0.2*(1-SSIM) at [1,3,H,W]; torch_ops = the reference's formulation (loss.py:27-117) on this GPU"}
 
 
 def ref_gpu_run(cfg_name, steps):

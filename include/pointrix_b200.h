@@ -168,6 +168,33 @@ int pxb_nvls_allreduce(void* mc_ptr, long long n_f32, long long n_i32, int rank,
 int pxb_p2p_allreduce(const void* const* peer_ptrs, long long n_f32, long long n_i32, int rank, int world,
                       void* stream);
 
+/* ---- photometric loss at the render boundary: replaces l1_loss / l2_loss / ssim
+ *      (pointrix/model/loss.py:27-67, 73-117) and their autograd, as called by BaseModel.get_loss_dict
+ *      (pointrix/model/base_model.py:113-120).  Images are [B,C,H,W] fp32 contiguous; window 11, sigma 1.5,
+ *      zero padding 5 (loss.py:100-108).  ws: pxb_loss_workspace_bytes(B,C,H,W) bytes of scratch.
+ *      l1_mean[B], ssim_mean[B]: per-image means over C*H*W (deterministic fixed-order reduction).
+ *      dmaps: NULL (no backward will follow) or [3,B,C,H,W] receiving dSSIM/dE[x], dSSIM/dE[xx], dSSIM/dE[xy].
+ *      pxb_l1_ssim_loss_forward: the training loss in the same pass, loss3 = {(1-l)*L1 + l*(1-SSIM), L1, 1-SSIM}
+ *      with means over the whole batch (base_model.py:117-120).
+ *      Backward: d_pred = w_ssim[b] * dSSIM_sum_b/dpred + w_l1[b] * sign(pred-gt) with
+ *      w_x[b] = s_x * g_x[b*g_stride]: g_* are DEVICE arrays (NULL = 0; g_stride 0 broadcasts one scalar), s_*
+ *      host scales, so the upstream gradient never has to reach the host. ---- */
+size_t pxb_loss_workspace_bytes(int B, int C, int H, int W);
+int pxb_l1_ssim_forward(int B, int C, int H, int W, const float* pred, const float* gt, float* dmaps, float* l1_mean,
+                        float* ssim_mean, void* ws, size_t ws_bytes, void* stream);
+int pxb_l1_ssim_loss_forward(int B, int C, int H, int W, const float* pred, const float* gt, float lambda_ssim,
+                             float* dmaps, float* loss3, void* ws, size_t ws_bytes, void* stream);
+int pxb_l1_ssim_backward(int B, int C, int H, int W, const float* pred, const float* gt, const float* dmaps,
+                         const float* g_l1, const float* g_ssim, int g_stride, float s_l1, float s_ssim, float* d_pred,
+                         void* stream);
+/* mode 1 = |pred-gt| (l1_loss), 2 = (pred-gt)^2 (l2_loss); n = elements per image.  map_out: NULL or [B*n]
+ * (return_mean=False); mean_out[B].  ws: at least 4*B*min(ceil(n/256), 1184) bytes of scratch.  Backward:
+ * d_pred = (w[b] + g_map[i]) * d loss/d pred, either of w (device [B]) / g_map (device [B*n]) may be NULL. */
+int pxb_pixel_loss_forward(int mode, int B, long long n, const float* pred, const float* gt, float* map_out,
+                           float* mean_out, void* ws, size_t ws_bytes, void* stream);
+int pxb_pixel_loss_backward(int mode, int B, long long n, const float* pred, const float* gt, const float* w,
+                            const float* g_map, float* d_pred, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -15,6 +15,12 @@ Two sources, both the reference itself:
       (GPU box) runs the compiled unmodified reference CUDA (oracle/_ref) on a small
       seeded scene through its own op order and stores every intermediate and gradient
       -> tests/golden/ref_gpu_small.npz (written to gpurun_out/ on the box and copied).
+
+  python oracle/make_golden.py --from-ref-loss
+      (this container, CPU) imports the reference's OWN pointrix/model/loss.py where it lies (its
+      `lpips` import, an absent third-party package the L1/SSIM code never touches, is stubbed),
+      runs l1_loss / l2_loss / psnr / ssim and the get_loss_dict combination with autograd on small
+      seeded images and stores inputs, values and gradients in tests/golden/ref_loss.npz.
 """
 from __future__ import annotations
 
@@ -150,8 +156,54 @@ def from_ref_gpu(out_path):
     print("wrote", out_path)
 
 
+def from_ref_loss(out_path):
+    sys.modules.setdefault("lpips", types.ModuleType("lpips"))
+    spec = importlib.util.spec_from_file_location("ref_loss", "/root/reference/pointrix/model/loss.py")
+    L = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(L)
+    G = {}
+    g = torch.Generator().manual_seed(5)
+    # (tag, shape): ragged sizes around the 32x32 tile and the 11-tap window, a 3-D image, smooth + noisy content
+    cases = [("a", (2, 3, 37, 53)), ("b", (1, 3, 64, 96)), ("c", (3, 1, 9, 7)), ("d", (3, 40, 33)), ("e", (1, 4, 1, 1))]
+    for tag, shp in cases:
+        gt = torch.rand(shp, generator=g)
+        if tag in ("a", "b"):  # a smooth ground truth and a prediction near it, like a half-trained render
+            yy, xx = torch.meshgrid(torch.linspace(0, 3, shp[-2]), torch.linspace(0, 4, shp[-1]), indexing="ij")
+            gt = (0.5 + 0.4 * torch.sin(xx + 2 * yy)).expand(shp).clone() + 0.05 * torch.rand(shp, generator=g)
+            pred = (gt + 0.1 * torch.randn(shp, generator=g)).clamp(0, 1)
+        else:
+            pred = torch.rand(shp, generator=g)
+        G[f"{tag}_pred"], G[f"{tag}_gt"] = pred, gt
+        p1 = pred.clone().requires_grad_()
+        l1 = L.l1_loss(p1, gt)
+        l1.backward()
+        G[f"{tag}_l1"], G[f"{tag}_l1_grad"] = l1.detach(), p1.grad
+        p2 = pred.clone().requires_grad_()
+        l2 = L.l2_loss(p2, gt)
+        l2.backward()
+        G[f"{tag}_l2"], G[f"{tag}_l2_grad"] = l2.detach(), p2.grad
+        G[f"{tag}_l1_map"] = L.l1_loss(pred, gt, return_mean=False)
+        if len(shp) == 4:
+            G[f"{tag}_psnr"] = L.psnr(pred, gt)
+            G[f"{tag}_ssim_per_image"] = L.ssim(pred, gt, size_average=False)
+        p3 = pred.clone().requires_grad_()
+        s = L.ssim(p3, gt)
+        s.backward()
+        G[f"{tag}_ssim"], G[f"{tag}_ssim_grad"] = s.detach(), p3.grad
+        # BaseModel.get_loss_dict (base_model.py:117-120) with lambda_ssim = 0.2
+        p4 = pred.clone().requires_grad_()
+        loss = (1.0 - 0.2) * L.l1_loss(p4, gt) + 0.2 * (1.0 - L.ssim(p4, gt))
+        loss.backward()
+        G[f"{tag}_loss"], G[f"{tag}_loss_grad"] = loss.detach(), p4.grad
+    G["window"] = L.create_window(11, 1)[0, 0]
+    np.savez_compressed(out_path, **{k: v.detach().cpu().numpy() for k, v in G.items()})
+    print("wrote", out_path, {k: tuple(v.shape) for k, v in G.items() if k.endswith("_pred")})
+
+
 if __name__ == "__main__":
-    if "--from-ref-tests" in sys.argv:
+    if "--from-ref-loss" in sys.argv:
+        from_ref_loss(os.path.join(ROOT, "tests", "golden", "ref_loss.npz"))
+    elif "--from-ref-tests" in sys.argv:
         from_ref_tests(os.path.join(ROOT, "tests", "golden", "ref_test_oracles.npz"))
     elif "--from-ref-gpu" in sys.argv:
         out = sys.argv[-1] if sys.argv[-1].endswith(".npz") else os.path.join(ROOT, "gpurun_out", "ref_gpu_small.npz")

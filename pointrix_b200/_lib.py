@@ -48,6 +48,12 @@ SIGNATURES = {
     "pxb_nvls_allreduce": (i32, [p, i64, i64, i32, i32, p]),
     "pxb_p2p_allreduce": (i32, [p, i64, i64, i32, i32, p]),
     "pxb_fused_backward": (i32, [i32, i32, p, p, p, p, i32, i32, p, p, p, i32, i32, i32, p, p, p, p, p, p, p, p, p, p, p, p]),
+    "pxb_loss_workspace_bytes": (sz, [i32, i32, i32, i32]),
+    "pxb_l1_ssim_forward": (i32, [i32, i32, i32, i32, p, p, p, p, p, p, sz, p]),
+    "pxb_l1_ssim_loss_forward": (i32, [i32, i32, i32, i32, p, p, f32, p, p, p, sz, p]),
+    "pxb_l1_ssim_backward": (i32, [i32, i32, i32, i32, p, p, p, p, p, i32, f32, f32, p, p]),
+    "pxb_pixel_loss_forward": (i32, [i32, i32, i64, p, p, p, p, p, sz, p]),
+    "pxb_pixel_loss_backward": (i32, [i32, i32, i64, p, p, p, p, p, p]),
 }
 
 if not os.path.exists(LIB_PATH):
@@ -90,6 +96,7 @@ KERNELS_PER_CALL = {
     "pxb_compute_sh_forward": 1, "pxb_compute_sh_backward": 1, "pxb_bin_prepare": 14, "pxb_sort_gaussian": 8,
     "pxb_pack_records": 1, "pxb_unpack_grads": 1, "pxb_blend_forward": 1, "pxb_blend_backward": 1,
     "pxb_fused_forward": 1, "pxb_fused_backward": 1,
+    "pxb_l1_ssim_forward": 2, "pxb_l1_ssim_loss_forward": 2, "pxb_l1_ssim_backward": 1, "pxb_pixel_loss_forward": 2, "pxb_pixel_loss_backward": 1,
 }
 
 

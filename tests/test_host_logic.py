@@ -62,6 +62,20 @@ def test_cpu_tensors_are_rejected():
                       torch.zeros(4, 3), torch.zeros(4, 4), torch.zeros(4, 16, 3))
 
 
+def test_loss_module_mirrors_reference_and_rejects_cpu():
+    """pointrix_b200.loss keeps the names of pointrix/model/loss.py and has no CPU path."""
+    from pointrix_b200 import loss
+
+    for name in ("l1_loss", "l2_loss", "psnr", "ssim", "gaussian", "create_window", "l1_ssim_loss", "get_loss_dict"):
+        assert callable(getattr(loss, name))
+    w = loss.create_window(11, 3)
+    assert w.shape == (3, 1, 11, 11) and abs(float(w[0, 0].sum()) - 1.0) < 1e-6
+    x = torch.rand(1, 3, 16, 16)
+    for fn in (loss.l1_loss, loss.l2_loss, loss.ssim, loss.l1_ssim_loss, loss.psnr):
+        with pytest.raises(RuntimeError, match="must be a CUDA tensor"):
+            fn(x, x)
+
+
 def test_no_oracle_on_the_product_path():
     """The package never imports oracle/ (CPU restatement) -- there is no fallback."""
     import pathlib
