@@ -134,7 +134,7 @@ int pxb_fused_backward(int P, int sh_degree, const float* pos, const float* scal
  *      call and reads it after the call returns (spinning while it is -1): a value > N_cap means the
  *      lists were truncated and the call must be repeated with a larger capacity, otherwise the
  *      outputs are exact.  stage_events: NULL, or 5 cudaEvent_t recorded before the first and after each
- *      of the four stages (per-stage timing).  ws: pxb_render_workspace_bytes(P, N_cap, W, H) bytes,
+ *      of the four stages (per-stage timing; a NULL entry is skipped).  ws: pxb_render_workspace_bytes(P, N_cap, W, H) bytes,
  *      256-byte aligned, scratch (nothing in it is needed by the backward).
  *      Saved for the backward: rec[P,S], depth[P], radius[P], idx_sorted, tile_range, final_T, ncontrib. ---- */
 size_t pxb_render_workspace_bytes(int P, long long N_cap, int W, int H);

@@ -65,15 +65,31 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
     return t;  // valid in thread 0
 }
 
-// loads the (42 x 42) halo tile of one image plane into shared memory, zero outside the image
+// loads the (42 x 42) halo tile of one image plane into shared memory, zero outside the image: warp = row,
+// lane = column (two columns per lane), all 12 loads of a thread issued before the first store
 __device__ __forceinline__ void load_halo(float (*dst)[kLP], const float* __restrict__ plane, int H, int W, int x0,
                                           int y0) {
-    for (int i = threadIdx.x; i < kLI * kLP; i += kLThreads) {
-        const int r = i / kLP, c = i - r * kLP;
-        const int gy = y0 + r - kLR, gx = x0 + c - kLR;
-        float v = 0.f;
-        if (c < kLI && gy >= 0 && gy < H && gx >= 0 && gx < W) v = __ldg(plane + (size_t)gy * W + gx);
-        dst[r][c] = v;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr int kRounds = (kLI + kLThreads / 32 - 1) / (kLThreads / 32);  // 6
+    const int gx0 = x0 + lane - kLR, gx1 = gx0 + 32;
+    const bool ok0 = gx0 >= 0 && gx0 < W, ok1 = lane < kLP - 32 && gx1 < W;  // gx1 >= 27 always
+    float v0[kRounds], v1[kRounds];
+#pragma unroll
+    for (int i = 0; i < kRounds; i++) {
+        const int r = warp + i * (kLThreads / 32);
+        const int gy = y0 + r - kLR;
+        const bool rok = r < kLI && gy >= 0 && gy < H;
+        const float* row = plane + (size_t)(rok ? gy : 0) * W;
+        v0[i] = rok && ok0 ? __ldg(row + gx0) : 0.f;
+        v1[i] = rok && ok1 && lane < kLI - 32 ? __ldg(row + gx1) : 0.f;
+    }
+#pragma unroll
+    for (int i = 0; i < kRounds; i++) {
+        const int r = warp + i * (kLThreads / 32);
+        if (r < kLI) {
+            dst[r][lane] = v0[i];
+            if (lane < kLP - 32) dst[r][lane + 32] = v1[i];
+        }
     }
 }
 

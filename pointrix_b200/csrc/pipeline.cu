@@ -34,7 +34,7 @@ WsRender carve(void* ws, int P, long long N_cap, int W, int H) {
 }
 
 inline int mark(void* const* ev, int i, cudaStream_t s) {
-    return ev ? (int)cudaEventRecord((cudaEvent_t)ev[i], s) : 0;
+    return ev && ev[i] ? (int)cudaEventRecord((cudaEvent_t)ev[i], s) : 0;  // NULL entry: stage not timed
 }
 
 }  // namespace

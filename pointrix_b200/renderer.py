@@ -101,12 +101,27 @@ def _wait_count(word) -> int:
                 raise RuntimeError("pointrix_b200: the binning kernels never reported an intersection count")
 
 
-def _stage_events(n: int):
-    """n timing events with live handles (torch creates the CUDA event on the first record)."""
-    evs = [torch.cuda.Event(enable_timing=True) for _ in range(n)]
+def _stage_events(timer, names):
+    """Timing events around the stages `names` (consecutive stages of one foreign call) the timer wants:
+    (events or None per boundary, the void*[len(names)+1] the native code records, NULL = skip)."""
+    if timer is None:
+        return None, None
+    n = len(names) + 1
+    need = [False] * n
+    for k, name in enumerate(names):
+        if timer.wants(name):
+            need[k] = need[k + 1] = True
+    if not any(need):
+        return None, None
+    evs = [torch.cuda.Event(enable_timing=True) if f else None for f in need]
     for e in evs:
-        e.record()
-    return evs, (C.c_void_p * n)(*[e.cuda_event for e in evs])
+        if e is not None:
+            e.record()  # torch creates the CUDA event on the first record
+    return evs, (C.c_void_p * n)(*[e.cuda_event if e is not None else None for e in evs])
+
+
+_FWD_STAGES = ("pxb_fused_forward", "pxb_bin_prepare", "pxb_sort_gaussian", "pxb_blend_forward")
+_BWD_STAGES = ("pxb_blend_backward", "pxb_fused_backward")
 
 
 class _FusedRender(torch.autograd.Function):
@@ -151,7 +166,7 @@ class _FusedRender(torch.autograd.Function):
                     del _WORKSPACE[k]  # one live workspace per (device, stream)
                 ws = _WORKSPACE[wkey] = E((lib.pxb_render_workspace_bytes(P, cap, W, H),), dtype=torch.uint8, device=dev)
             idx_sorted = E((cap,), dtype=i32, device=dev)
-            evs, ev_arr = _stage_events(5) if timer is not None else (None, None)
+            evs, ev_arr = _stage_events(timer, _FWD_STAGES)
             word.value = -1
             args = (P, int(sh_degree), _p(pos), _p(sc), _p(rot), _p(op), _p(sh), _p(ex), n_extra, int(with_depth),
                     _p(intr_c), _p(extr_c), _p(cc), W, H, float(nearest), 1.3, float(bg), S, cap, _p(rec), _p(depth),
@@ -165,9 +180,10 @@ class _FusedRender(torch.autograd.Function):
             _lib.count_launches("pxb_render_forward", W, H)
             n = _wait_count(word)
             ops.LAST_N[(dev.index, True)] = n
-            if timer is not None:
-                for k, name in enumerate(("pxb_fused_forward", "pxb_bin_prepare", "pxb_sort_gaussian", "pxb_blend_forward")):
-                    timer.events.append((name, evs[k], evs[k + 1]))
+            if evs is not None:
+                for k, name in enumerate(_FWD_STAGES):
+                    if timer.wants(name):
+                        timer.events.append((name, evs[k], evs[k + 1]))
             if n <= cap:
                 if 2 * n < cap:  # shrink slowly when the scene got much lighter
                     _CAPACITY[ckey] = max(int(n * 1.25) + 65536, int(cap * 0.9))
@@ -208,16 +224,17 @@ class _FusedRender(torch.autograd.Function):
         timer = _lib._timer
         base = flat.data_ptr()
         with torch.cuda.device(dev):
-            evs, ev_arr = _stage_events(3) if timer is not None else (None, None)
+            evs, ev_arr = _stage_events(timer, _BWD_STAGES)
             _lib.check(lib.pxb_render_backward(
                 P, sh_degree, _p(pos), _p(sc), _p(rot), _p(sh), n_extra, with_depth, _p(intr), _p(extr), _p(cc), W, H, bg,
                 S, _p(rec), _p(depth), _p(radius), _p(idx_sorted), _p(tile_range), _p(final_T), _p(ncontrib), _p(g),
                 _p(grec), base + 4 * 52 * P, base + 4 * 55 * P, base + 4 * 48 * P, base + 4 * 58 * P, base,
                 _p(d_extra), base + 4 * 59 * P, _p(d_cam), ev_arr, _raw_stream(dev.index)), "pxb_render_backward")
         _lib.count_launches("pxb_render_backward", W, H)
-        if timer is not None:
-            timer.events.append(("pxb_blend_backward", evs[0], evs[1]))
-            timer.events.append(("pxb_fused_backward", evs[1], evs[2]))
+        if evs is not None:
+            for k, name in enumerate(_BWD_STAGES):
+                if timer.wants(name):
+                    timer.events.append((name, evs[k], evs[k + 1]))
         d_intr = d_cam[0:4].reshape(s_intr) if ctx.needs_input_grad[6] else None
         d_extr = d_cam[4:16].reshape(s_extr) if ctx.needs_input_grad[7] else None
         d_cc = d_cam[16:19].reshape(s_cc) if ctx.needs_input_grad[8] else None
