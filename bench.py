@@ -231,6 +231,7 @@ def _main(out_f):
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ref-gpu", action="store_true")
     ap.add_argument("--no-loss-leg", action="store_true")
+    ap.add_argument("--exchange", default="factored", choices=["factored", "allreduce", "nccl"])
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args, out_f)
@@ -267,14 +268,23 @@ def _main(out_f):
         from pointrix_b200 import renderer as _renderer_mod
 
         try:
-            exch = parallel.NvlsGradExchange(P, dev)
+            if args.exchange == "nccl":
+                raise RuntimeError("NCCL requested")
+            if args.exchange == "factored":
+                exch = parallel.ShFactoredExchange(P, dev)
+                exch_kind = (f"SH gradient rebuilt from every rank's dL/drgb read over NVLink (pxb_sh_grad_gather), "
+                             f"13 floats/Gaussian + radii all-reduced in symmetric memory ({exch.mode})")
+            else:
+                exch = parallel.NvlsGradExchange(P, dev)
+                exch_kind = f"pxb_{exch.mode}_allreduce of 61 floats/Gaussian + radii over symmetric memory"
             _renderer_mod.set_grad_sink(exch)
-            exch_kind = f"pxb_{exch.mode}_allreduce over symmetric memory"
         except Exception as e:  # noqa: BLE001
             exch, exch_kind = None, f"NCCL all-reduce ({type(e).__name__})"
 
     def exchange(out, rw):
-        if exch is not None:
+        if isinstance(exch, parallel.ShFactoredExchange):
+            exch.exchange(out["radii"], params["position"])
+        elif exch is not None:
             exch.exchange(out["radii"])
         else:
             parallel.allreduce_step([p_.grad for p_ in params.values()], out["uv_points"].grad, out["radii"], world,
@@ -520,7 +530,7 @@ def _main(out_f):
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_name(args.config), "intersections_reference_lists": N_ref,
                    "intersections_binned": N_mean,
-                   "parallelism": f"view-sharded dp{world}" + (f", all-reduce of 59+2 floats/Gaussian + max(radii) per step: {exch_kind}" if world > 1 else ""),
+                   "parallelism": f"view-sharded dp{world}" + (f", gradients of 59+2 floats/Gaussian summed + max(radii) per step: {exch_kind}" if world > 1 else ""),
                    "cache": "inputs larger than L2 (236 MB Gaussian table + 48 MB records vs 126 MB L2); a different view every step"},
         "render_mpix_s": round(render_mpix, 2),
         "e2e": {"value": round(e2e_value, 3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},

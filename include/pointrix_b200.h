@@ -124,7 +124,7 @@ int pxb_fused_backward(int P, int sh_degree, const float* pos, const float* scal
                        const float* shs, int n_extra, int with_depth, const float* intr, const float* extr,
                        const float* cam_center, int W, int H, int S, const float* depth, const int* radius,
                        const float* grec, float* d_pos, float* d_scales, float* d_quats, float* d_opacity,
-                       float* d_shs, float* d_extra, float* d_ndc, float* d_cam, void* stream);
+                       float* d_shs, float* d_rgb, float* d_extra, float* d_ndc, float* d_cam, void* stream);
 
 /* ---- one view of MsplatRender.render_iter behind ONE call each way
  *      (pointrix/model/renderer/msplat.py:94-151 and its autograd graph): pxb_fused_forward (tight
@@ -145,14 +145,17 @@ int pxb_render_forward(int P, int sh_degree, const float* pos, const float* scal
                        int* idx_sorted, int* tile_range, float* final_T, int* ncontrib, float* out, int* total_host,
                        void* ws, size_t ws_bytes, void* const* stage_events, void* stream);
 /* grec[P,S]: scratch (zeroed inside); d_cam[19] or NULL (zeroed inside); stage_events: NULL or 3 events
- * (before blend backward, between, after the per-Gaussian backward). */
+ * (before blend backward, between, after the per-Gaussian backward).
+ * d_rgb: NULL, or [P,3] receiving the clamp-gated dL/drgb INSTEAD of d_shs (which may then be NULL): the
+ * factored form of the SH gradient, d_shs = basis(dir) (x) d_rgb, that pxb_sh_grad_gather sums over the
+ * views of a data-parallel step. */
 int pxb_render_backward(int P, int sh_degree, const float* pos, const float* scales, const float* quats,
                         const float* shs, int n_extra, int with_depth, const float* intr, const float* extr,
                         const float* cam_center, int W, int H, float bg, int S, const float* rec, const float* depth,
                         const int* radius, const int* idx_sorted, const int* tile_range, const float* final_T,
                         const int* ncontrib, const float* dL_dout, float* grec, float* d_pos, float* d_scales,
-                        float* d_quats, float* d_opacity, float* d_shs, float* d_extra, float* d_ndc, float* d_cam,
-                        void* const* stage_events, void* stream);
+                        float* d_quats, float* d_opacity, float* d_shs, float* d_rgb, float* d_extra, float* d_ndc,
+                        float* d_cam, void* const* stage_events, void* stream);
 
 /* ---- data-parallel gradient exchange (all-reduce(SUM) of the parameter gradients and
  *      ndc.grad, all-reduce(MAX) of radii; the reference's equivalent is batch_size = world on one GPU,
@@ -167,6 +170,14 @@ int pxb_nvls_allreduce(void* mc_ptr, long long n_f32, long long n_i32, int rank,
  * Preferred for world = 2 and when the group has no multicast support. */
 int pxb_p2p_allreduce(const void* const* peer_ptrs, long long n_f32, long long n_i32, int rank, int world,
                       void* stream);
+/* SH gradient of a data-parallel step without exchanging it: every rank published, in its symmetric replica
+ * (peer_ptrs: HOST array of `world` replica base pointers in rank order), the clamp-gated dL/drgb [P,3] of its
+ * view at float offset rgb_offset and its camera centre (3 floats) at float offset cam_offset
+ * (pxb_render_backward with d_rgb).  Writes d_shs[P,16,3] = sum over ranks q of basis(dir(pos, centre_q)) (x)
+ * d_rgb_q (zero above sh_degree), reading the peers over NVLink inside the kernel; identical bits on all ranks.
+ * The caller brackets it with the same cross-rank barriers as the all-reduce. */
+int pxb_sh_grad_gather(const void* const* peer_ptrs, long long rgb_offset, long long cam_offset, int world, int P,
+                       int sh_degree, const float* pos, float* d_shs, void* stream);
 
 /* ---- photometric loss at the render boundary: replaces l1_loss / l2_loss / ssim
  *      (pointrix/model/loss.py:27-67, 73-117) and their autograd, as called by BaseModel.get_loss_dict

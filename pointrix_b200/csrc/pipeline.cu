@@ -79,8 +79,8 @@ int pxb_render_backward(int P, int sh_degree, const float* pos, const float* sca
                         const float* cam_center, int W, int H, float bg, int S, const float* rec, const float* depth,
                         const int* radius, const int* idx_sorted, const int* tile_range, const float* final_T,
                         const int* ncontrib, const float* dL_dout, float* grec, float* d_pos, float* d_scales,
-                        float* d_quats, float* d_opacity, float* d_shs, float* d_extra, float* d_ndc, float* d_cam,
-                        void* const* stage_events, void* stream) {
+                        float* d_quats, float* d_opacity, float* d_shs, float* d_rgb, float* d_extra, float* d_ndc,
+                        float* d_cam, void* const* stage_events, void* stream) {
     cudaStream_t s = (cudaStream_t)stream;
     const int C = 3 + (with_depth ? 1 : 0) + n_extra;
     if (P <= 0 || W <= 0 || H <= 0) return PXB_ERR_BAD_ARG;
@@ -92,8 +92,8 @@ int pxb_render_backward(int P, int sh_degree, const float* pos, const float* sca
     if (rc) return rc;
     if ((rc = mark(stage_events, 1, s))) return rc;
     rc = pxb_fused_backward(P, sh_degree, pos, scales, quats, shs, n_extra, with_depth, intr, extr, cam_center, W, H, S,
-                            depth, radius, grec, d_pos, d_scales, d_quats, d_opacity, d_shs, d_extra, d_ndc, d_cam,
-                            stream);
+                            depth, radius, grec, d_pos, d_scales, d_quats, d_opacity, d_shs, d_rgb, d_extra, d_ndc,
+                            d_cam, stream);
     if (rc) return rc;
     return mark(stage_events, 2, s);
 }

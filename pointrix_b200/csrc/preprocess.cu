@@ -532,8 +532,8 @@ fused_bwd_kernel(int P, const float* __restrict__ pos, const float* __restrict__
                  const float* __restrict__ cam_center, int W, int H, int S, const float* __restrict__ depth,
                  const int* __restrict__ radius, const float* __restrict__ grec, float* __restrict__ d_pos,
                  float* __restrict__ d_scales, float4* __restrict__ d_quats, float* __restrict__ d_opacity,
-                 float* __restrict__ d_shs, float* __restrict__ d_extra, float* __restrict__ d_ndc,
-                 float* __restrict__ d_cam /*[19]: intr4, extr12, center3 or null*/) {
+                 float* __restrict__ d_shs, float* __restrict__ d_rgb /*[P,3] or null*/, float* __restrict__ d_extra,
+                 float* __restrict__ d_ndc, float* __restrict__ d_cam /*[19]: intr4, extr12, center3 or null*/) {
     extern __shared__ __align__(16) float sh_smem[];
     __shared__ float red[19 * (kFThreads / 32)];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -641,9 +641,15 @@ fused_bwd_kernel(int P, const float* __restrict__ pos, const float* __restrict__
                 o[3 * k] = o[3 * k + 1] = o[3 * k + 2] = 0.f;
             }
         }
-        float4* dst = reinterpret_cast<float4*>(d_shs + (size_t)i * 48);
+        if (d_rgb != nullptr) {
+            // factored form for the data-parallel exchange (exchange.cu, sh_grad_gather_kernel): dL/dshs of
+            // this view is the outer product basis(dir) x gated dL/drgb, so only the 3-vector leaves the kernel
+            d_rgb[3 * i] = gr3[0]; d_rgb[3 * i + 1] = gr3[1]; d_rgb[3 * i + 2] = gr3[2];
+        } else {
+            float4* dst = reinterpret_cast<float4*>(d_shs + (size_t)i * 48);
 #pragma unroll
-        for (int q = 0; q < 12; q++) dst[q] = make_float4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
+            for (int q = 0; q < 12; q++) dst[q] = make_float4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
+        }
         // normalize backward: d = v/|v|
         const float dot = ddx * dx + ddy * dy + ddz * dz;
         const float vx = (ddx - dx * dot) * inv, vy = (ddy - dy * dot) * inv, vz = (ddz - dz * dot) * inv;
@@ -654,6 +660,106 @@ fused_bwd_kernel(int P, const float* __restrict__ pos, const float* __restrict__
         d_quats[i] = make_float4(dq[0], dq[1], dq[2], dq[3]);
     }
     if (d_cam != nullptr) block_reduce_atomic<19>(cg, d_cam, red);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// SH gradient of a data-parallel step, summed over the views of all ranks WITHOUT exchanging it:
+// dL/dshs[g] of one view is the outer product  basis(dir(g, camera)) (x) gated dL/drgb[g]  (fused_bwd_kernel
+// above), so instead of all-reducing 48 floats per Gaussian the ranks publish 3 (their d_rgb, in symmetric
+// memory) plus their camera centre, and every rank rebuilds  sum_q basis(dir_q) (x) d_rgb_q  itself: this
+// kernel reads the peers' d_rgb straight over NVLink (plain peer loads; the sum runs in rank order, so all
+// ranks hold identical bits) while it does the math, and writes the finished [P,16,3] gradient locally.
+// Bytes over NVLink per Gaussian: 12 (world - 1) in, against 192 * 2 (world - 1) / world for the all-reduce.
+struct GatherPeers {
+    const float* p[16];
+};
+
+template <int KA>
+__global__ void __launch_bounds__(256, 3)
+sh_grad_gather_kernel(GatherPeers peers, long long rgb_off, long long cam_off, int world, int P,
+                      const float* __restrict__ pos, float* __restrict__ d_shs) {
+    // Persistent CTAs walk blocks of 256 Gaussians (= 768 consecutive d_rgb floats per peer), 4 peers per
+    // round.  Peer loads are NVLink round trips, so they are few and wide (coalesced 16 bytes, staged through
+    // shared memory) and those of the NEXT (block, round) are already in flight while this one is computed.
+    __shared__ __align__(16) float s_rgb[4][768];
+    __shared__ float s_cam[16][3];
+    const int tid = threadIdx.x;
+    const long long n3 = 3ll * P;
+    const int nblk = (P + 255) / 256;
+    if (tid < 3 * world) s_cam[tid / 3][tid % 3] = __ldcg(peers.p[tid / 3] + cam_off + tid % 3);
+
+    float4 v[4];
+    auto issue = [&](int blk_i, int q0) {
+        const long long e = 768ll * blk_i + 4 * tid;
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (tid < 192 && q0 + u < world) {
+                const float* src = peers.p[q0 + u] + rgb_off + e;
+                if (e + 3 < n3) {
+                    v[u] = __ldcg(reinterpret_cast<const float4*>(src));
+                } else {  // tail of the last block
+                    if (e < n3) v[u].x = __ldcg(src);
+                    if (e + 1 < n3) v[u].y = __ldcg(src + 1);
+                    if (e + 2 < n3) v[u].z = __ldcg(src + 2);
+                }
+            }
+        }
+    };
+
+    int blk_i = blockIdx.x, q0 = 0;
+    if (blk_i < nblk) issue(blk_i, q0);
+    float px = 0.f, py = 0.f, pz = 0.f;
+    float acc[3 * KA];
+    while (blk_i < nblk) {
+        if (tid < 192) {
+#pragma unroll
+            for (int u = 0; u < 4; u++) *reinterpret_cast<float4*>(&s_rgb[u][4 * tid]) = v[u];
+        }
+        __syncthreads();
+        int nb = blk_i, nq = q0 + 4;
+        if (nq >= world) { nq = 0; nb = blk_i + gridDim.x; }
+        if (nb < nblk) issue(nb, nq);
+        const int i = blk_i * 256 + tid;
+        if (q0 == 0) {
+            if (i < P) { px = pos[3 * i]; py = pos[3 * i + 1]; pz = pos[3 * i + 2]; }
+#pragma unroll
+            for (int k = 0; k < 3 * KA; k++) acc[k] = 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int q = q0 + u;
+            if (q < world) {
+                const float r0 = s_rgb[u][3 * tid], r1 = s_rgb[u][3 * tid + 1], r2 = s_rgb[u][3 * tid + 2];
+                if (r0 != 0.f || r1 != 0.f || r2 != 0.f) {
+                    // same direction arithmetic as fused_bwd_kernel
+                    float dx = px - s_cam[q][0], dy = py - s_cam[q][1], dz = pz - s_cam[q][2];
+                    const float inv = 1.0f / sqrtf(dx * dx + dy * dy + dz * dz);
+                    dx *= inv; dy *= inv; dz *= inv;
+                    float B[KA];
+                    sh_basis<KA>(dx, dy, dz, B);
+#pragma unroll
+                    for (int k = 0; k < KA; k++) {
+                        acc[3 * k] = fmaf(r0, B[k], acc[3 * k]);
+                        acc[3 * k + 1] = fmaf(r1, B[k], acc[3 * k + 1]);
+                        acc[3 * k + 2] = fmaf(r2, B[k], acc[3 * k + 2]);
+                    }
+                }
+            }
+        }
+        if (q0 + 4 >= world && i < P) {
+            float4* dst = reinterpret_cast<float4*>(d_shs + (size_t)i * 48);
+#pragma unroll
+            for (int q = 0; q < 12; q++) {
+                float o[4];
+#pragma unroll
+                for (int e = 0; e < 4; e++) o[e] = (4 * q + e) < 3 * KA ? acc[(4 * q + e) < 3 * KA ? 4 * q + e : 0] : 0.f;
+                dst[q] = make_float4(o[0], o[1], o[2], o[3]);
+            }
+        }
+        __syncthreads();
+        blk_i = nb; q0 = nq;
+    }
 }
 
 }  // namespace pxb
@@ -800,9 +906,10 @@ int pxb_fused_backward(int P, int sh_degree, const float* pos, const float* scal
                        const float* shs, int n_extra, int with_depth, const float* intr, const float* extr,
                        const float* cam_center, int W, int H, int S, const float* depth, const int* radius,
                        const float* grec, float* d_pos, float* d_scales, float* d_quats, float* d_opacity,
-                       float* d_shs, float* d_extra, float* d_ndc, float* d_cam, void* stream) {
+                       float* d_shs, float* d_rgb, float* d_extra, float* d_ndc, float* d_cam, void* stream) {
     if (P <= 0) return 0;
     if (sh_degree < 0 || sh_degree > 3) return PXB_ERR_UNSUPPORTED;
+    if (d_shs == nullptr && d_rgb == nullptr) return PXB_ERR_BAD_ARG;
     if ((((uintptr_t)shs) | ((uintptr_t)grec) | ((uintptr_t)quats) | ((uintptr_t)d_shs) | ((uintptr_t)d_quats)) & 15)
         return PXB_ERR_ALIGN;
     cudaStream_t s = (cudaStream_t)stream;
@@ -812,7 +919,7 @@ int pxb_fused_backward(int P, int sh_degree, const float* pos, const float* scal
     fused_bwd_kernel<KA><<<nb, kFThreads, smem, s>>>(P, pos, scales, (const float4*)quats, shs, n_extra,         \
                                                      with_depth, intr, extr, cam_center, W, H, S, depth, radius, \
                                                      grec, d_pos, d_scales, (float4*)d_quats, d_opacity, d_shs,  \
-                                                     d_extra, d_ndc, d_cam)
+                                                     d_rgb, d_extra, d_ndc, d_cam)
     switch (sh_degree) {
         case 0: PXB_LAUNCH_BWD(1); break;
         case 1: PXB_LAUNCH_BWD(4); break;
@@ -820,6 +927,32 @@ int pxb_fused_backward(int P, int sh_degree, const float* pos, const float* scal
         default: PXB_LAUNCH_BWD(16); break;
     }
 #undef PXB_LAUNCH_BWD
+    return (int)cudaGetLastError();
+}
+
+int pxb_sh_grad_gather(const void* const* peer_ptrs, long long rgb_offset, long long cam_offset, int world, int P,
+                       int sh_degree, const float* pos, float* d_shs, void* stream) {
+    if (peer_ptrs == nullptr || world < 1 || world > 16 || rgb_offset < 0 || cam_offset < 0 || !pos || !d_shs)
+        return PXB_ERR_BAD_ARG;
+    if (P <= 0) return 0;
+    if (sh_degree < 0 || sh_degree > 3) return PXB_ERR_UNSUPPORTED;
+    if (((uintptr_t)d_shs) & 15) return PXB_ERR_ALIGN;
+    GatherPeers gp;
+    for (int q = 0; q < 16; q++) gp.p[q] = q < world ? (const float*)peer_ptrs[q] : nullptr;
+    for (int q = 0; q < world; q++)
+        if (gp.p[q] == nullptr) return PXB_ERR_BAD_ARG;
+    cudaStream_t s = (cudaStream_t)stream;
+    int nb = (P + 255) / 256;
+    if (nb > 148 * 3) nb = 148 * 3;  // persistent: 3 resident CTAs per SM
+#define PXB_LAUNCH_GATHER(KA) \
+    sh_grad_gather_kernel<KA><<<nb, 256, 0, s>>>(gp, rgb_offset, cam_offset, world, P, pos, d_shs)
+    switch (sh_degree) {
+        case 0: PXB_LAUNCH_GATHER(1); break;
+        case 1: PXB_LAUNCH_GATHER(4); break;
+        case 2: PXB_LAUNCH_GATHER(9); break;
+        default: PXB_LAUNCH_GATHER(16); break;
+    }
+#undef PXB_LAUNCH_GATHER
     return (int)cudaGetLastError();
 }
 

@@ -62,7 +62,10 @@ _GRAD_SINK = None
 
 def set_grad_sink(sink) -> None:
     """``sink.next_buffer(numel) -> Tensor | None`` supplies the buffer the fused backward writes the
-    P-sized gradients into (None: allocate).  Pass None to detach."""
+    P-sized gradients into (None: allocate).  A sink with ``plan(P, device, cam_center, sh_degree)`` returns
+    ``(d_shs, d_rot, d_pos, d_scale, d_opacity, d_ndc, d_rgb)`` instead (or None to decline); with a
+    non-None ``d_rgb[P,3]`` the backward writes the factored SH gradient there and leaves ``d_shs`` to
+    the sink's exchange.  Pass None to detach."""
     global _GRAD_SINK
     _GRAD_SINK = sink
 
@@ -208,28 +211,35 @@ class _FusedRender(torch.autograd.Function):
         g = _f32(d_out, "dL_drendered")
         grec = torch.empty((P, S), dtype=torch.float32, device=dev)  # zeroed by the call
         # every P-sized gradient lives in ONE flat buffer (the 16-byte-aligned blocks first), so a
-        # data-parallel caller exchanges them with a single collective (parallel.allreduce_step)
-        flat = _GRAD_SINK.next_buffer(61 * P) if _GRAD_SINK is not None else None
-        if flat is None or flat.device != dev:
-            flat = torch.empty(61 * P, dtype=torch.float32, device=dev)
-        d_sh = flat[0:48 * P].view(P, 16, 3)
-        d_rot = flat[48 * P:52 * P].view(P, 4)
-        d_pos = flat[52 * P:55 * P].view(P, 3)
-        d_sc = flat[55 * P:58 * P].view(P, 3)
-        d_op = flat[58 * P:59 * P]
-        d_ndc = flat[59 * P:61 * P].view(P, 2)
+        # data-parallel caller exchanges them with a single collective (parallel.allreduce_step); a sink
+        # may instead supply the buffers itself (symmetric memory) and ask for the factored SH gradient
+        plan = None
+        if _GRAD_SINK is not None and hasattr(_GRAD_SINK, "plan"):
+            plan = _GRAD_SINK.plan(P, dev, cc, sh_degree)
+        if plan is not None:
+            d_sh, d_rot, d_pos, d_sc, d_op, d_ndc, d_rgb = plan
+        else:
+            flat = _GRAD_SINK.next_buffer(61 * P) if _GRAD_SINK is not None else None
+            if flat is None or flat.device != dev:
+                flat = torch.empty(61 * P, dtype=torch.float32, device=dev)
+            d_sh = flat[0:48 * P].view(P, 16, 3)
+            d_rot = flat[48 * P:52 * P].view(P, 4)
+            d_pos = flat[52 * P:55 * P].view(P, 3)
+            d_sc = flat[55 * P:58 * P].view(P, 3)
+            d_op = flat[58 * P:59 * P]
+            d_ndc = flat[59 * P:61 * P].view(P, 2)
+            d_rgb = None
         d_extra = torch.empty(P, n_extra, dtype=torch.float32, device=dev) if n_extra > 0 else None
         need_cam = any(ctx.needs_input_grad[6:9])
         d_cam = torch.empty(19, dtype=torch.float32, device=dev) if need_cam else None
         timer = _lib._timer
-        base = flat.data_ptr()
         with torch.cuda.device(dev):
             evs, ev_arr = _stage_events(timer, _BWD_STAGES)
             _lib.check(lib.pxb_render_backward(
                 P, sh_degree, _p(pos), _p(sc), _p(rot), _p(sh), n_extra, with_depth, _p(intr), _p(extr), _p(cc), W, H, bg,
                 S, _p(rec), _p(depth), _p(radius), _p(idx_sorted), _p(tile_range), _p(final_T), _p(ncontrib), _p(g),
-                _p(grec), base + 4 * 52 * P, base + 4 * 55 * P, base + 4 * 48 * P, base + 4 * 58 * P, base,
-                _p(d_extra), base + 4 * 59 * P, _p(d_cam), ev_arr, _raw_stream(dev.index)), "pxb_render_backward")
+                _p(grec), _p(d_pos), _p(d_sc), _p(d_rot), _p(d_op), _p(None if d_rgb is not None else d_sh), _p(d_rgb),
+                _p(d_extra), _p(d_ndc), _p(d_cam), ev_arr, _raw_stream(dev.index)), "pxb_render_backward")
         _lib.count_launches("pxb_render_backward", W, H)
         if evs is not None:
             for k, name in enumerate(_BWD_STAGES):

@@ -21,8 +21,9 @@ def _worker(rank, world, port, q):
     from pointrix_b200 import parallel, renderer, scene
 
     P, W, H = 20000, 320, 240
+    STEPS = 3  # consecutive steps through the same exchange object: its 2 buffers rotate and get reused
     c, sc, _ = scene.make_config("cfg1", P=P, views=world)
-    cams = scene.make_cameras(world, W, H, seed=1)
+    cams = scene.make_cameras(STEPS * world, W, H, seed=1)
     dimg = scene.upstream_gradient(3, H, W).to(dev) / world  # mean over the batch
     r = pb.parse_renderer({"name": "MsplatRender"}, white_bg=True, device=str(dev))
     r.sh_degree = 3
@@ -39,23 +40,42 @@ def _worker(rank, world, port, q):
         renderer.set_grad_sink(None)
         return params, outs
 
-    # reference semantics: this rank alone renders ALL views (autograd accumulates the gradients)
-    p_all, o_all = run(range(world), None)
-    ndc_sum = sum(o["uv_points"].grad for o in o_all)
-    radii_max = torch.stack([o["radii"] for o in o_all]).max(dim=0).values
+    # reference semantics: this rank alone renders ALL views of a step (autograd accumulates the gradients)
+    refs = []
+    for s in range(STEPS):
+        p_all, o_all = run(range(s * world, (s + 1) * world), None)
+        refs.append((p_all, sum(o["uv_points"].grad for o in o_all),
+                     torch.stack([o["radii"] for o in o_all]).max(dim=0).values))
+    p_all, ndc_sum, radii_max = refs[0]
     res = {}
-    for mode in ("p2p", "nvls"):
+    for kind, mode in (("allreduce", "p2p"), ("allreduce", "nvls"), ("factored", "p2p"), ("factored", "nvls")):
         try:
-            ex = parallel.NvlsGradExchange(P, dev, mode=mode)
+            ex = (parallel.NvlsGradExchange if kind == "allreduce" else parallel.ShFactoredExchange)(P, dev, mode=mode)
         except RuntimeError:
-            res[mode] = None  # no multicast on this box
+            res[f"{kind}-{mode}"] = None  # no multicast on this box
             continue
-        p_mine, o_mine = run([rank], ex)
-        vis = ex.exchange(o_mine[0]["radii"])
-        torch.cuda.synchronize()
-        errs = {k: ((p_mine[k].grad - p_all[k].grad).norm() / p_all[k].grad.norm().clamp_min(1e-30)).item() for k in p_all}
-        errs["ndc"] = ((o_mine[0]["uv_points"].grad - ndc_sum).norm() / ndc_sum.norm()).item()
-        res[mode] = (errs, bool(torch.equal(o_mine[0]["radii"], radii_max)), bool(torch.equal(vis, radii_max > 0)))
+        worst, radii_ok, vis_ok, same_bits = {}, True, True, True
+        for s in range(STEPS):
+            pa, ns, rm = refs[s]
+            p_mine, o_mine = run([s * world + rank], ex)
+            if kind == "allreduce":
+                vis = ex.exchange(o_mine[0]["radii"])
+            else:
+                vis = ex.exchange(o_mine[0]["radii"], p_mine["position"])
+            torch.cuda.synchronize()
+            errs = {k: ((p_mine[k].grad - pa[k].grad).norm() / pa[k].grad.norm().clamp_min(1e-30)).item() for k in pa}
+            errs["ndc"] = ((o_mine[0]["uv_points"].grad - ns).norm() / ns.norm()).item()
+            for k, e in errs.items():
+                worst[k] = max(worst.get(k, 0.0), e)
+            radii_ok &= bool(torch.equal(o_mine[0]["radii"], rm))
+            vis_ok &= bool(torch.equal(vis, rm > 0))
+            # every rank must hold identical bits (fixed summation order)
+            chk = torch.stack([p_mine[k].grad.double().sum() for k in sorted(p_mine)])
+            allc = [torch.empty_like(chk) for _ in range(world)]
+            dist.all_gather(allc, chk)
+            same_bits &= all(bool(torch.equal(a, allc[0])) for a in allc)
+        worst["ranks_differ"] = 0.0 if same_bits else 1.0
+        res[f"{kind}-{mode}"] = (worst, radii_ok, vis_ok)
     # the NCCL path of the same step
     p_mine, o_mine = run([rank], None)
     parallel.allreduce_step([p.grad for p in p_mine.values()], o_mine[0]["uv_points"].grad, o_mine[0]["radii"], world,
@@ -66,15 +86,16 @@ def _worker(rank, world, port, q):
     dist.destroy_process_group()
 
 
-def test_world2_exchange_equals_one_rank_batch():
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs 2 GPUs")
+@pytest.mark.parametrize("world", [2, 4])
+def test_exchange_equals_one_rank_batch(world):
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
     import torch.multiprocessing as mp
 
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29700 + (os.getpid() % 200)
-    ps = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    port = 29700 + (os.getpid() % 200) + world
+    ps = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
     for p in ps:
         p.start()
     out = [q.get(timeout=300) for _ in ps]
@@ -86,7 +107,7 @@ def test_world2_exchange_equals_one_rank_batch():
             if v is None:
                 continue
             errs, radii_ok, vis_ok = v
-            assert radii_ok and vis_ok, (rank, mode)
+            assert radii_ok and vis_ok, (rank, mode, errs)
             for k, e in errs.items():
                 # atomics order differs between runs: the same tolerance as the single-GPU gradient parity
                 assert e <= 1e-3, (rank, mode, k, e)
