@@ -86,7 +86,7 @@ def _worker(rank, world, port, q):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world", [2, 4])
+@pytest.mark.parametrize("world", [2, 4, 8])
 def test_exchange_equals_one_rank_batch(world):
     if torch.cuda.device_count() < world:
         pytest.skip(f"needs {world} GPUs")
