@@ -3,11 +3,21 @@
 1920x1080, SH degree 3, through the MsplatRender plugin (pointrix_b200).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config cfg4]
+                    [--exchange factored|allreduce|nccl] [--no-cpu-baseline] [--no-ref-gpu] [--no-loss-leg]
 
 One "step" = one training iteration of the render path on one view per GPU:
 MsplatRender.render_iter forward, then backward of <dL/dimg, img> with a fixed
-random dL/dimg into every Gaussian parameter (+ NCCL all-reduce of the parameter
-gradients / ndc gradients / radii when N > 1, views sharded by rank).
+random dL/dimg into every Gaussian parameter (+ when N > 1, views sharded by rank, the
+exchange that leaves the batch gradients / ndc gradients / radii on every rank: by default the
+SH-factored exchange over symmetric memory, parallel.ShFactoredExchange).
+
+Timed regions: (1) `value`: K device-resident steps, CUDA events, barrier + synchronize on both
+sides, max over ranks; only the dominant kernel is bracketed by events inside it (`roofline`),
+a second pass of K steps times every stage (`roofline_stages`).  (2) `render_mpix_s`: K forward-only
+views.  (3) `e2e`: K steps with the view's camera and dL/dimg coming from pinned HOST memory and
+the loss read back on the host every step.  (4) `photometric_loss` (N = 1): the fused L1+SSIM loss
+beside the reference's torch-op formulation, and render -> loss -> backward.  (5) `cpu_baseline`,
+`ref_gpu` (N = 1): the CPU oracle on a bounded sample and the compiled reference CUDA on this GPU.
 
 `--impl reference` times the CPU-PyTorch restatement of the same math (the oracle) on
 the host cores on a bounded sample of the same workload (the reference has no CPU
