@@ -550,7 +550,7 @@ def _main(out_f):
     }
     if loss_info is not None:
         line["photometric_loss"] = loss_info
-    if not args.no_cpu_baseline:
+    if world == 1 and not args.no_cpu_baseline:  # rank 0 at N = 1 only (the other ranks of a larger run have left)
         line["cpu_baseline"] = cpu_oracle_run(args.config, args.cpu_sample, 2, 1)
     if world == 1 and not args.no_ref_gpu:
         line["ref_gpu"] = ref_gpu_run(args.config, min(K, 10))

@@ -47,13 +47,16 @@ def _no_gt_grad(gt: Tensor) -> None:
 # l1 / l2                  pointrix/model/loss.py:27-67
 # ---------------------------------------------------------------------------
 class _PixelLoss(torch.autograd.Function):
-    """mode 1: |pred-gt|, mode 2: (pred-gt)^2; returns (per-image means [B], map or empty)."""
+    """mode 1: |pred-gt|, mode 2: (pred-gt)^2; returns (means [B], map or empty) with B = the first
+    dimension (per-image means, psnr) or 1 (one global mean, l1_loss / l2_loss)."""
 
     @staticmethod
-    def forward(ctx, pred, gt, mode, want_map):
+    def forward(ctx, pred, gt, mode, want_map, per_image):
         p, g = _f32(pred, "pred"), _f32(gt, "gt")
         dev = p.device
-        B = p.shape[0] if p.dim() > 1 else 1
+        B = p.shape[0] if (per_image and p.dim() > 1) else 1
+        if B > 65535:
+            raise RuntimeError(f"per-image losses support up to 65535 images, got {B}")
         n = p.numel() // B
         means = torch.empty(B, dtype=torch.float32, device=dev)
         vmap = torch.empty_like(p) if want_map else None
@@ -78,16 +81,16 @@ class _PixelLoss(torch.autograd.Function):
         d = torch.empty_like(p)
         with torch.cuda.device(dev):
             launch("pxb_pixel_loss_backward", ctx.mode, ctx.B, ctx.n, _p(p), _p(g), _p(w), _p(gm), _p(d), _stream(dev))
-        return d.view(ctx.shape), None, None, None
+        return d.view(ctx.shape), None, None, None, None
 
 
 def _pixel_loss(pred: Tensor, gt: Tensor, mode: int, return_mean: bool) -> Tensor:
     assert pred.shape == gt.shape, "The shape of the two tensor should be the same."
     _no_gt_grad(gt)
-    means, vmap = _PixelLoss.apply(pred, gt, mode, not return_mean)
+    means, vmap = _PixelLoss.apply(pred, gt, mode, not return_mean, False)
     if not return_mean:
         return vmap.view(pred.shape)
-    return means.mean()  # equal-sized images: the mean of the per-image means is the global mean
+    return means.reshape(())
 
 
 def l1_loss(pred: Tensor, gt: Tensor, return_mean: bool = True) -> Tensor:
@@ -103,7 +106,7 @@ def l2_loss(pred: Tensor, gt: Tensor, return_mean: bool = True) -> Tensor:
 def psnr(img_pred: Tensor, img_gt: Tensor) -> Tensor:
     """Per-image PSNR ``[B,1]`` for images in [0,1]; loss.py:10-25."""
     assert img_pred.shape == img_gt.shape, "The shape of the two images should be the same."
-    means, _ = _PixelLoss.apply(img_pred, img_gt, 2, False)
+    means, _ = _PixelLoss.apply(img_pred, img_gt, 2, False, True)
     return 20 * torch.log10(1.0 / torch.sqrt(means.view(-1, 1)))
 
 
