@@ -183,3 +183,61 @@ def test_coalesce_leaves_unrelated_tensors_alone():
     flat = torch.zeros(10)
     gap = parallel._coalesce([flat[0:4], flat[6:10]])  # not contiguous: two collectives
     assert len(gap) == 2
+
+
+def _worker_factored(rank, world, port, q):
+    """The SH-factored exchange protocol (parallel.ShFactoredExchange) restated with gloo collectives and the
+    CPU oracle: all-reduce 13 floats + all-gather (d_rgb, camera centre) + local rebuild == all-reduce of all 61."""
+    import torch.distributed as dist
+
+    from oracle import msplat_oracle as O
+    from pointrix_b200 import scene
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    P, W, H, deg = 300, 64, 48, 3
+    c, sc, _ = scene.make_config("cfg1", P=P, views=1)
+    cams = scene.make_cameras(world, W, H, seed=1)
+    leaves = {k: v.clone().requires_grad_() for k, v in sc.items()}
+    o = O.render_iter(H, W, cams["extrinsic_matrix"][rank], cams["intrinsic_params"], cams["camera_center"][rank],
+                      **leaves, sh_degree=deg)
+    dimg = scene.upstream_gradient(3, H, W, seed=2) / world
+    (o["rendered_features_split"]["rgb"] * dimg).sum().backward()
+    # what the 61-float all-reduce leaves on every rank
+    full = {k: v.grad.clone() for k, v in leaves.items()}
+    for t in full.values():
+        dist.all_reduce(t)
+    # factored: the SH gradient never travels.  The gated dL/drgb of this view is its DC row / C0.
+    d_rgb = leaves["shs"].grad[:, 0, :] / 0.28209479177387814
+    rgbs = [torch.empty_like(d_rgb) for _ in range(world)]
+    cens = [torch.empty(3) for _ in range(world)]
+    dist.all_gather(rgbs, d_rgb.contiguous())
+    dist.all_gather(cens, cams["camera_center"][rank].contiguous())
+    rebuilt = torch.zeros(P, 16, 3)
+    for r_, c_ in zip(rgbs, cens):  # rank order: identical bits on every rank
+        d = sc["position"] - c_.reshape(1, 3)
+        d = d / d.norm(dim=1, keepdim=True)
+        rebuilt += O.sh_bases(16, d)[:, :16, None] * r_[:, None, :]
+    err = ((rebuilt - full["shs"]).norm() / full["shs"].norm()).item()
+    chk = rebuilt.double().sum().reshape(1)
+    allc = [torch.empty_like(chk) for _ in range(world)]
+    dist.all_gather(allc, chk)
+    q.put((rank, err, bool(all(torch.equal(a, allc[0]) for a in allc)), float(full["shs"].abs().sum())))
+    dist.destroy_process_group()
+
+
+def test_factored_exchange_protocol_gloo_world2():
+    import torch.multiprocessing as mp
+
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 33500 + (os.getpid() % 2000)
+    ps = [ctx.Process(target=_worker_factored, args=(r, 2, port, q)) for r in range(2)]
+    for p in ps:
+        p.start()
+    res = [q.get(timeout=240) for _ in ps]
+    for p in ps:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, err, same_bits, mag in res:
+        assert mag > 0 and err <= 1e-5 and same_bits, (rank, err, same_bits)
