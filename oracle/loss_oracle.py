@@ -1,7 +1,8 @@
 """CPU restatement of the reference's photometric loss -- TEST INFRASTRUCTURE ONLY.
 
-Only tests/, __graft_entry__.smoke() and bench.py's CPU legs may import this module; the product
-(pointrix_b200/) never does.  Plain PyTorch on CPU tensors, each function citing the reference lines
+Only tests/, __graft_entry__.smoke() and bench.py's baseline legs may import this module (bench.py times
+it as "the reference's torch-op formulation" beside the fused kernels, never as part of them; tools/ are
+developer scripts); the product (pointrix_b200/) never does.  Plain PyTorch on CPU tensors, each function citing the reference lines
 it follows.  Pinned: tests/golden/ref_loss.npz holds inputs, values and autograd gradients produced by
 the reference's own pointrix/model/loss.py imported where it lies (generator:
 `python oracle/make_golden.py --from-ref-loss`), and tests/test_oracle.py checks this file against them.
