@@ -3,7 +3,7 @@
  *
  * Drop-in boundary: these entry points are what a binding for the reference's
  * 12 `msplat._C` functions (msplat/msplat/src/ext.cpp:14-25; C++ signatures in
- * msplat/msplat/include/*.h) would call, expressed with plain device pointers,
+ * msplat/msplat/include/<op>.h) would call, expressed with plain device pointers,
  * sizes and a CUDA stream -- no torch types.  Every function returns 0 on
  * success, a cudaError_t value (>0) on a CUDA failure or a PXB_ERR_* code (<0)
  * on a bad argument; nothing throws across the boundary.
