@@ -37,34 +37,42 @@ def psnr(img_pred, img_gt):
 
 
 def window_1d(window_size=11, sigma=1.5):
-    # gaussian(), pointrix/model/loss.py:69-71: python-double exp, fp32 tensor, fp32 normalisation
-    g = torch.tensor([exp(-(x - window_size // 2) ** 2 / float(2 * sigma ** 2)) for x in range(window_size)],
-                     dtype=torch.float32)
-    return g / g.sum()
+    """The reference's 1-D window (gaussian(), pointrix/model/loss.py:69-71): each tap is a Python-double
+    exp rounded to fp32, the normalisation an fp32 division by the fp32 sum."""
+    half = window_size // 2
+    taps = [exp(-((i - half) ** 2) / float(2 * sigma ** 2)) for i in range(window_size)]
+    w = torch.tensor(taps, dtype=torch.float32)
+    return w / w.sum()
+
+
+def _box(x, kernel):
+    # depthwise "same" filtering with zero padding: F.conv2d(..., padding=ws//2, groups=C), loss.py:100-108
+    return F.conv2d(x, kernel, padding=kernel.shape[-1] // 2, groups=x.size(-3))
 
 
 def ssim(img1, img2, window_size=11, size_average=True):
-    # ssim() + _ssim() + create_window(), pointrix/model/loss.py:73-123
-    channel = img1.size(-3)
-    w1 = window_1d(window_size).unsqueeze(1)
-    window = w1.mm(w1.t()).float().unsqueeze(0).unsqueeze(0).expand(channel, 1, window_size, window_size).contiguous()
-    window = window.type_as(img1)
-    pad = window_size // 2
-    mu1 = F.conv2d(img1, window, padding=pad, groups=channel)
-    mu2 = F.conv2d(img2, window, padding=pad, groups=channel)
-    mu1_sq, mu2_sq, mu1_mu2 = mu1.pow(2), mu2.pow(2), mu1 * mu2
-    sigma1_sq = F.conv2d(img1 * img1, window, padding=pad, groups=channel) - mu1_sq
-    sigma2_sq = F.conv2d(img2 * img2, window, padding=pad, groups=channel) - mu2_sq
-    sigma12 = F.conv2d(img1 * img2, window, padding=pad, groups=channel) - mu1_mu2
-    C1, C2 = 0.01 ** 2, 0.03 ** 2
-    ssim_map = ((2 * mu1_mu2 + C1) * (2 * sigma12 + C2)) / ((mu1_sq + mu2_sq + C1) * (sigma1_sq + sigma2_sq + C2))
+    """ssim() + _ssim() + create_window() of pointrix/model/loss.py:73-123 as one function: the 2-D window is
+    the fp32 outer product of the 1-D window, one copy per channel; the SSIM map is
+    (2 mu_x mu_y + C1)(2 cov + C2) / ((mu_x^2 + mu_y^2 + C1)(var_x + var_y + C2)) with C1 = 0.01^2, C2 = 0.03^2."""
+    n_ch = img1.size(-3)
+    w = window_1d(window_size)
+    kernel = torch.outer(w, w).to(img1.dtype).expand(n_ch, 1, window_size, window_size).contiguous()
+    mean_x, mean_y = _box(img1, kernel), _box(img2, kernel)
+    var_x = _box(img1 * img1, kernel) - mean_x * mean_x
+    var_y = _box(img2 * img2, kernel) - mean_y * mean_y
+    cov = _box(img1 * img2, kernel) - mean_x * mean_y
+    c1, c2 = 0.01 ** 2, 0.03 ** 2
+    numer = (2 * (mean_x * mean_y) + c1) * (2 * cov + c2)
+    denom = (mean_x * mean_x + mean_y * mean_y + c1) * (var_x + var_y + c2)
+    smap = numer / denom
     if size_average:
-        return ssim_map.mean()
-    return ssim_map.mean(1).mean(1).mean(1)
+        return smap.mean()
+    return smap.mean(1).mean(1).mean(1)  # per image, the reference's nested means (loss.py:117)
 
 
 def l1_ssim_loss(pred, gt, lambda_ssim=0.2):
-    # BaseModel.get_loss_dict, pointrix/model/base_model.py:113-124
-    L1 = l1_loss(pred, gt)
-    sl = 1.0 - ssim(pred, gt)
-    return {"loss": (1.0 - lambda_ssim) * L1 + lambda_ssim * sl, "L1_loss": L1, "ssim_loss": sl}
+    """BaseModel.get_loss_dict, pointrix/model/base_model.py:113-124."""
+    l1 = l1_loss(pred, gt)
+    one_minus_ssim = 1.0 - ssim(pred, gt)
+    total = (1.0 - lambda_ssim) * l1 + lambda_ssim * one_minus_ssim
+    return {"loss": total, "L1_loss": l1, "ssim_loss": one_minus_ssim}

@@ -114,15 +114,19 @@ def psnr(img_pred: Tensor, img_gt: Tensor) -> Tensor:
 # ssim                     pointrix/model/loss.py:69-123
 # ---------------------------------------------------------------------------
 def gaussian(window_size: int, sigma: float) -> Tensor:
-    gauss = torch.Tensor([exp(-(x - window_size // 2) ** 2 / float(2 * sigma ** 2)) for x in range(window_size)])
-    return gauss / gauss.sum()
+    """Normalised 1-D Gaussian window, bit-identical to the reference's (loss.py:69-71): Python-double taps
+    rounded to fp32, then an fp32 division by their fp32 sum.  Host helper."""
+    centre = window_size // 2
+    taps = torch.tensor([exp(-((k - centre) ** 2) / float(2 * sigma ** 2)) for k in range(window_size)],
+                        dtype=torch.float32)
+    return taps / taps.sum()
 
 
 def create_window(window_size: int, channel: int) -> Tensor:
-    """The reference's [channel,1,ws,ws] window (host helper; the kernels apply it separably)."""
-    w1 = gaussian(window_size, 1.5).unsqueeze(1)
-    w2 = w1.mm(w1.t()).float().unsqueeze(0).unsqueeze(0)
-    return w2.expand(channel, 1, window_size, window_size).contiguous()
+    """The reference's [channel,1,ws,ws] depthwise window (loss.py:119-123): outer product of the 1-D window
+    (sigma 1.5) with itself.  Host helper; the kernels apply the 1-D window separably."""
+    w = gaussian(window_size, 1.5)
+    return torch.outer(w, w).expand(channel, 1, window_size, window_size).contiguous()
 
 
 class _L1Ssim(torch.autograd.Function):
