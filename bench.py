@@ -195,7 +195,11 @@ def run_reference(args, out_f):
     rank = env_int("RANK", 0)
     if rank != 0:
         return
-    r = cpu_oracle_run(args.config, args.cpu_sample, max(1, min(args.steps, 3)), min(args.warmup, 1))
+    # bounded: at most 3 timed iterations after at most 1 warm-up, whatever K and W are (2.5 s per iteration on
+    # the sample), so the arm ends within a minute; the line says so
+    n_timed, n_warm = max(1, min(args.steps, 3)), min(args.warmup, 1)
+    r = cpu_oracle_run(args.config, args.cpu_sample, n_timed, n_warm)
+    r["timed_iterations"], r["warmup_iterations"] = n_timed, n_warm
     line = {"metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1000.0 / r["value"], "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
