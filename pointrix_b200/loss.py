@@ -10,14 +10,12 @@ image); the ground truth is treated as a constant, which is how the reference us
 """
 from __future__ import annotations
 
-import ctypes as C
 from math import exp
 from typing import Dict, Optional
 
 import torch
 from torch import Tensor
 
-from . import _lib
 from ._lib import launch, lib
 from .ops import _f32, _p, _stream
 
