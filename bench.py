@@ -367,13 +367,24 @@ def _main(out_f):
     stage_timer = _lib.KernelTimer()
     _lib.set_timer(stage_timer)
     s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    step_marks = [torch.cuda.Event(enable_timing=True) for _ in range(K + 1)]  # per-step boundaries (this pass only)
     s0.record()
+    step_marks[0].record()
     for s in range(K):
         step_fn(W_ + K + s)
+        step_marks[s + 1].record()
     s1.record()
     sync()
     _lib.set_timer(None)
     ms_stage_pass = s0.elapsed_time(s1)
+    step_dist = None
+    try:  # distribution of the per-step device time (median, p10, p90); never fatal
+        per = sorted(step_marks[i].elapsed_time(step_marks[i + 1]) for i in range(K))
+        pick = lambda q: round(per[min(K - 1, max(0, int(round(q * (K - 1)))))], 4)  # noqa: E731
+        step_dist = {"p10": pick(0.10), "median": pick(0.50), "p90": pick(0.90), "min": round(per[0], 4),
+                     "max": round(per[-1], 4), "pass": "stage-timing pass (this rank)"}
+    except Exception as e:  # noqa: BLE001
+        step_dist = {"unavailable": repr(e)[:120]}
     t = torch.tensor([ms], device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -550,6 +561,7 @@ def _main(out_f):
         "e2e": {"value": round(e2e_value, 3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "roofline_stages": stages,
         "roofline_stages_note": f"second pass of {K} steps with every stage bracketed by CUDA events ({round(ms_stage_pass / K, 4)} ms/step)",
+        "step_ms_distribution": step_dist,
         "blend_issue_roofline": blend_issue,
     }
     if loss_info is not None:
