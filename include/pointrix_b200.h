@@ -110,6 +110,10 @@ int pxb_blend_forward(const float* rec, int S, int C, const int* idx_sorted, con
 int pxb_blend_backward(const float* rec, int S, int C, const int* idx_sorted, const int* tile_range, float bg, int W,
                        int H, const float* final_T, const int* ncontrib, const float* dL_dout, float* grec,
                        void* stream);
+/* Measurement aid (no reference counterpart): counters_dev = device pointer to >= 2 uint64 words, or NULL to
+ * switch counting off.  While set, slot 0 / slot 1 accumulate the (8x4 pixel block, Gaussian) candidates the
+ * warps of blend forward / backward launches executed (32 pixel-Gaussian pair tests each). */
+int pxb_blend_counters(unsigned long long* counters_dev);
 
 /* ---- fused per-Gaussian stages of MsplatRender.render_iter
  *      (pointrix/model/renderer/msplat.py:94-139 forward; its autograd graph backward).

@@ -56,7 +56,8 @@ def ssim(img1, img2, window_size=11, size_average=True):
     (2 mu_x mu_y + C1)(2 cov + C2) / ((mu_x^2 + mu_y^2 + C1)(var_x + var_y + C2)) with C1 = 0.01^2, C2 = 0.03^2."""
     n_ch = img1.size(-3)
     w = window_1d(window_size)
-    kernel = torch.outer(w, w).to(img1.dtype).expand(n_ch, 1, window_size, window_size).contiguous()
+    # window.type_as(img1) in the reference (loss.py:91-95): device AND dtype follow the image
+    kernel = torch.outer(w, w).to(device=img1.device, dtype=img1.dtype).expand(n_ch, 1, window_size, window_size).contiguous()
     mean_x, mean_y = _box(img1, kernel), _box(img2, kernel)
     var_x = _box(img1 * img1, kernel) - mean_x * mean_x
     var_y = _box(img2 * img2, kernel) - mean_y * mean_y

@@ -331,6 +331,7 @@ def compute_sh(shs, view_dirs, visible: Optional[torch.Tensor] = None):
 def alpha_blending(
     uv, conic, opacity, feature, idx_sorted, tile_range, bg: float, W: int, H: int,
     ndc: Optional[torch.Tensor] = None, return_aux: bool = False, max_elems: int = 1 << 24,
+    dL_dout: Optional[torch.Tensor] = None,
 ):
     """Front-to-back blend per 16x16 tile, vectorised over (tiles-in-chunk, 256
     pixels, list length).  Skip rules (alpha_blending.cu:80-94): power > 0;
@@ -340,6 +341,13 @@ def alpha_blending(
     ``ndc`` (if given, requires_grad) receives dL/duv * (W/2, H/2) exactly as
     msplat/msplat/alpha_blending.py:106-110 does: it enters the graph through a
     zero-valued term whose Jacobian is that scale.
+
+    ``dL_dout`` ([C,H,W], optional): bounded-memory backward.  Every tile chunk is back-propagated as
+    soon as it is blended (``autograd.backward(chunk, dL_dout[chunk])``, accumulating into the ``.grad`` of
+    whatever leaves ``uv / conic / opacity / feature`` hang off) and its graph is dropped, so the
+    [tiles, 256, list] intermediates of only ONE chunk are alive at a time; the returned image is
+    detached.  Used by :func:`render_step` for the full-size CPU baseline (1 M Gaussians at 1080p would
+    otherwise keep > 100 GB of autograd state).
     """
     C = feature.shape[1]
     gx, gy = (W + BLOCK - 1) // BLOCK, (H + BLOCK - 1) // BLOCK
@@ -362,6 +370,10 @@ def alpha_blending(
     pieces_out, pieces_T, pieces_n, pieces_tile = [], [], [], []
     i = 0
     idx_sorted = idx_sorted.to(torch.int64)
+    dL_pad = None
+    if dL_dout is not None:  # [C,H,W] -> tile-padded [gy*16, gx*16, C]
+        dL_pad = torch.zeros(gy * BLOCK, gx * BLOCK, C, dtype=feature.dtype, device=dev)
+        dL_pad[:H, :W] = dL_dout.detach().permute(1, 2, 0)
     while i < order.numel():
         # chunk of tiles with similar list lengths
         nmax = int(counts[order[min(i + 63, order.numel() - 1)]])
@@ -407,7 +419,14 @@ def alpha_blending(
         Fpix = torch.einsum("tpn,tnc->tpc", wgt, feature[g])
         Tf = T_incl2[..., -1]
         last = torch.where(alive, (k + 1)[None, None, :].expand_as(alive), torch.zeros_like(alive, dtype=torch.int64)).amax(-1)
-        pieces_out.append(Fpix + Tf[..., None] * bg)
+        piece = Fpix + Tf[..., None] * bg
+        if dL_pad is not None:
+            tyc = (tiles_c // gx)[:, None] * BLOCK + ly.long()[None, :]
+            txc = (tiles_c % gx)[:, None] * BLOCK + lx.long()[None, :]
+            if piece.requires_grad:
+                torch.autograd.backward(piece, dL_pad[tyc, txc])
+            piece, Tf = piece.detach(), Tf.detach()
+        pieces_out.append(piece)
         pieces_T.append(Tf)
         pieces_n.append(last.to(torch.int32))
         pieces_tile.append(tiles_c)
@@ -475,3 +494,42 @@ def render_iter(
         "_aux": {"uv": uv, "depth": depth, "conic": conic, "tiles": tiles, "idx_sorted": idx_sorted,
                  "tile_range": tile_range, "rgb": rgb},
     }
+
+
+def render_step(height: int, width: int, extrinsic_matrix, intrinsic_params, camera_center,
+                position, opacity, scaling, rotation, shs, loss_fn, sh_degree: int = 3, bg_color: float = 1.0) -> Dict:
+    """One training iteration of :func:`render_iter` + ``loss_fn(rgb[3,H,W]) -> scalar`` + backward with
+    bounded memory: the same math and the same gradients as ``loss_fn(render_iter(...)).backward()``, but
+    the blend is differentiated chunk by chunk (``alpha_blending(dL_dout=...)``) behind a detached
+    boundary, so full-size scenes fit the host.  Gradients land in ``.grad`` of the leaves passed in
+    (Gaussian parameters and, when they require grad, the camera tensors); returns
+    ``{"rgb", "loss", "radii", "ndc_grad"}``.
+    """
+    direction = position - camera_center.reshape(1, 3)
+    direction = direction / direction.norm(dim=1, keepdim=True)
+    sh_coeff = shs.permute(0, 2, 1)
+    sh_mask = torch.zeros_like(sh_coeff)
+    sh_mask[..., : (sh_degree + 1) ** 2] = 1.0
+    rgb = (compute_sh(sh_coeff * sh_mask, direction) + 0.5).clamp(min=0.0)
+    extr = extrinsic_matrix[:3, :]
+    uv, depth = project_point(position, intrinsic_params, extr, width, height, nearest=0.2)
+    visible = depth != 0
+    cov3d = compute_cov3d(scaling, rotation, visible)
+    conic, radius, tiles = ewa_project(position, cov3d, intrinsic_params, extr, uv, width, height, visible)
+    idx_sorted, tile_range = sort_gaussian(uv, depth, width, height, radius, tiles)
+    # detached boundary: the blend sees leaves of its own
+    b_uv, b_conic, b_op, b_feat = (t.detach().requires_grad_() for t in (uv, conic, opacity, rgb))
+    with torch.no_grad():
+        img = alpha_blending(b_uv, b_conic, b_op, b_feat, idx_sorted, tile_range, bg_color, width, height)
+    img.requires_grad_()
+    loss = loss_fn(img)
+    loss.backward()
+    alpha_blending(b_uv, b_conic, b_op, b_feat, idx_sorted, tile_range, bg_color, width, height, dL_dout=img.grad)
+    zero = torch.zeros_like
+    g = [b_uv.grad if b_uv.grad is not None else zero(b_uv), b_conic.grad if b_conic.grad is not None else zero(b_conic),
+         b_op.grad if b_op.grad is not None else zero(b_op), b_feat.grad if b_feat.grad is not None else zero(b_feat)]
+    # dL/duv reaches nothing upstream (ewa_project.py:84-85 returns None for uv; project_point gets it): feed
+    # the four boundary gradients back into the per-Gaussian graph
+    torch.autograd.backward([uv, conic, opacity, rgb], g)
+    scale = torch.tensor([0.5 * width, 0.5 * height], dtype=uv.dtype)
+    return {"rgb": img.detach(), "loss": loss.detach(), "radii": radius, "ndc_grad": g[0] * scale}

@@ -58,6 +58,17 @@ __device__ __forceinline__ unsigned int block_mask(float u, float v, float A, fl
     return m;
 }
 
+// Optional device counters (pxb_blend_counters): when the pointer is set, every warp adds the number of
+// (8x4 block, Gaussian) candidates it executed to slot 0 (forward) / 1 (backward) as it leaves -- one
+// 64-bit add per warp per launch.  bench.py derives the pair-test rate from them in an untimed pass.
+__device__ unsigned long long* g_blend_counters = nullptr;
+__device__ __forceinline__ void count_candidates(int slot, int n) {
+    if ((threadIdx.x & 31) == 0) {
+        unsigned long long* c = g_blend_counters;
+        if (c != nullptr) atomicAdd(c + slot, (unsigned long long)n);
+    }
+}
+
 #ifdef PXB_STATS
 __device__ unsigned long long g_blend_stats[8];
 #define PXB_STAT(i, v) do { if ((threadIdx.x & 31) == 0) atomicAdd(&g_blend_stats[i], (unsigned long long)(v)); } while (0)
@@ -163,6 +174,7 @@ blend_fwd_kernel(const float* __restrict__ rec, const int* __restrict__ idx_sort
     const unsigned int rec_s = opaque_u32((unsigned int)__cvta_generic_to_shared(sm_rec));
     const unsigned int list_s = opaque_u32((unsigned int)__cvta_generic_to_shared(my_list));
     write_sentinel(sm_rec, S);
+    int n_cand = 0;
 
     for (int base = 0; todo > 0; base += kBatch, todo -= kBatch) {
         if (__syncthreads_count(thr > 1.f) == kBlendThreads) break;
@@ -179,7 +191,8 @@ blend_fwd_kernel(const float* __restrict__ rec, const int* __restrict__ idx_sort
         const int cnt = build_candidates<true>(sm_mask, my_list, n, 0x40000000, 0x7fffffff);
         PXB_STAT(5, cnt);
         const int last_base = base + 1;
-        for (int c = 0; c < cnt; c += kUnroll) {
+        int c = 0;
+        for (; c < cnt; c += kUnroll) {
 #pragma unroll
             for (int u = 0; u < kUnroll; u++) {
                 const int j = (int)lds_u16(list_s + 2u * (unsigned)(c + u));
@@ -210,9 +223,11 @@ blend_fwd_kernel(const float* __restrict__ rec, const int* __restrict__ idx_sort
                     }
                 }
             }
-            if (__all_sync(0xffffffffu, thr > 1.f)) break;
+            if (__all_sync(0xffffffffu, thr > 1.f)) { c += kUnroll; break; }
         }
+        n_cand += min(c, cnt);
     }
+    count_candidates(0, n_cand);
     if (inside) {
         const size_t pix = (size_t)pyi * W + pxi;
         final_T[pix] = T;
@@ -389,6 +404,7 @@ blend_bwd_kernel(const float* __restrict__ rec, const int* __restrict__ idx_sort
         __syncthreads();
         // positions >= warp_last contribute to no pixel of this warp
         const int cnt = build_candidates<false>(sm_mask, my_list, n, top, warp_last);
+        count_candidates(1, cnt);  // per batch: a running total would cost the kernel its 64th register
         PXB_STAT(0, cnt);
         for (int c = 0; c < cnt; c++) {
             const int j = (int)lds_u16(list_s + 2u * (unsigned)c);
@@ -560,6 +576,12 @@ int pxb_blend_backward(const float* rec, int S, int C, const int* idx_sorted, co
     if (C < 1 || C > PXB_MAX_CHANNELS_PER_PASS || S != pxb_record_stride(C)) return PXB_ERR_BAD_ARG;
     if ((((uintptr_t)rec) | ((uintptr_t)grec)) & 15) return PXB_ERR_ALIGN;
     PXB_BLEND_DISPATCH(launch_bwd, rec, idx_sorted, tile_range, bg, C, W, H, final_T, ncontrib, dL_dout, grec, s)
+}
+
+// counters: device pointer to >= 2 unsigned 64-bit words (NULL switches counting off).  Slot 0 accumulates
+// the (8x4 block, Gaussian) candidates executed by blend forward launches, slot 1 by blend backward.
+int pxb_blend_counters(unsigned long long* counters_dev) {
+    return (int)cudaMemcpyToSymbol(g_blend_counters, &counters_dev, sizeof(counters_dev));
 }
 
 #ifdef PXB_STATS

@@ -153,9 +153,11 @@ def save_checkpoint(path, global_step: int, optimizer_state: dict, model_state: 
     torch.save(data, path)
 
 
-def load_checkpoint(path, map_location="cpu") -> dict:
-    """The dict ``BaseTrainer.load_model`` iterates over (``base_trainer.py:145-160``)."""
-    data = torch.load(path, map_location=map_location, weights_only=False)
+def load_checkpoint(path, map_location="cpu", weights_only: bool = True) -> dict:
+    """The dict ``BaseTrainer.load_model`` iterates over (``base_trainer.py:145-160``).  Tensors, numbers,
+    strings and containers only by default; ``weights_only=False`` (the reference's ``torch.load`` default
+    at the time, which executes arbitrary pickled code) is an explicit opt-in for trusted files."""
+    data = torch.load(path, map_location=map_location, weights_only=weights_only)
     if not isinstance(data, dict) or "global_step" not in data:
         raise ValueError(f"{path}: not a pointrix checkpoint")
     return data

@@ -51,9 +51,14 @@ def begin_radii_reduce(radii: torch.Tensor, world: int, group=None):
 
 def allreduce_step(param_grads: Sequence[torch.Tensor], ndc_grad: Optional[torch.Tensor], radii: torch.Tensor,
                    world: int, group=None, average: bool = True, radii_work=None) -> torch.Tensor:
-    """In-place exchange after a local backward.  Parameter gradients are averaged, ``ndc_grad``
-    summed, ``radii`` max-reduced; returns the batch visibility (``max radii > 0`` -- no collective
-    of its own is needed).  Works on NCCL and gloo.
+    """In-place exchange after a local backward.  ``radii`` is max-reduced; returns the batch visibility
+    (``max radii > 0`` -- no collective of its own is needed).  Works on NCCL and gloo.
+
+    ``average=True`` (each rank back-propagated its own un-scaled view loss): everything is scaled by
+    1/world and summed -- the parameter gradients become the mean over views AND every view's
+    ``ndc_grad`` carries 1/world before the sum, exactly as in the reference, where the batch loss is
+    a mean (pointrix/model/loss.py:27-46), so each view's ``ndc.grad`` already holds 1/B when
+    ``accumulate_viewspace_grad`` sums them (pointrix/controller/gs.py:274-278).
 
     ``average=False``: the caller's loss already carries the 1/world factor (the reference's mean
     over the stacked batch, pointrix/model/loss.py:27-46, applies it to every view's loss and
@@ -63,11 +68,11 @@ def allreduce_step(param_grads: Sequence[torch.Tensor], ndc_grad: Optional[torch
         return radii > 0
     works = []
     grads = [g for g in param_grads if g is not None]
+    bufs = grads + ([ndc_grad] if ndc_grad is not None else [])
     if average:
         inv = 1.0 / world
-        for g in grads:
+        for g in _coalesce(bufs):
             g.mul_(inv)
-    bufs = grads + ([ndc_grad] if ndc_grad is not None else [])
     for t in _coalesce(bufs):
         works.append(dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group, async_op=True))
     if radii_work is None:
@@ -135,6 +140,12 @@ class NvlsGradExchange:
     def next_buffer(self, numel: int) -> Optional[torch.Tensor]:
         if numel != 61 * self.P:
             return None
+        if self._cur is not None:
+            # the previous backward's gradients still alias buffer `_cur` (autograd adopted the views):
+            # a second backward would rotate onto / overwrite memory `.grad` points into
+            raise RuntimeError("NvlsGradExchange: one backward per exchange() -- the previous backward has not been "
+                               "exchanged yet (render_batch with several views per rank, or gradient accumulation, "
+                               "must use parallel.allreduce_step instead)")
         self._cur = self._next
         self._next = (self._next + 1) % len(self.bufs)
         return self.bufs[self._cur][:numel]
@@ -228,6 +239,10 @@ class ShFactoredExchange:
     def plan(self, P: int, dev, cam_center: torch.Tensor, sh_degree: int):
         if P != self.P or torch.device(dev) != self.device:
             return None
+        if self._cur is not None:
+            raise RuntimeError("ShFactoredExchange: one backward per exchange() -- the previous backward has not been "
+                               "exchanged yet (its d_rgb / camera centre would be lost and its gradient views "
+                               "overwritten); use parallel.allreduce_step for several views per rank")
         self._cur = self._next
         self._next = (self._next + 1) % len(self.bufs)
         buf = self.bufs[self._cur]

@@ -279,16 +279,23 @@ class MsplatRender(BaseObject):
 
     # ------------------------------------------------------------------
     def render_iter(self, height, width, extrinsic_matrix, intrinsic_params, camera_center, position, opacity,
-                    scaling, rotation, shs, **kwargs) -> dict:
-        """One view.  Extra per-Gaussian feature tensors ``[P,c]`` passed as keyword
-        arguments (e.g. ``normals``) are blended as additional channels and
-        returned under their keyword name (examples/supervise/renderer.py:25-102);
-        any other keyword is ignored, as in the reference."""
+                    scaling, rotation, shs, normals=None, extra_features: Optional[Dict[str, Tensor]] = None,
+                    **kwargs) -> dict:
+        """One view.  Extra per-Gaussian feature tensors ``[P,c]`` are blended as additional channels and
+        returned under their name: ``normals`` (the keyword of examples/supervise/renderer.py:25-102) and
+        any entry of the explicit ``extra_features`` dict (e.g. a 2-channel flow), in that order.  Every
+        other keyword is ignored, as in the reference (msplat.py:51-64 swallows ``**kwargs``)."""
         if not position.is_cuda:
             raise RuntimeError("position must be a CUDA tensor")
         P = position.shape[0]
-        extras = {k: v for k, v in kwargs.items()
-                  if isinstance(v, Tensor) and v.dim() == 2 and v.shape[0] == P and v.is_floating_point()}
+        extras: Dict[str, Tensor] = {}
+        if normals is not None:
+            extras["normals"] = normals
+        if extra_features:
+            extras.update(extra_features)
+        for k, v in extras.items():
+            if not (isinstance(v, Tensor) and v.dim() == 2 and v.shape[0] == P and v.is_floating_point()):
+                raise ValueError(f"extra feature {k!r} must be a floating [P,c] tensor")
         extra = torch.cat(list(extras.values()), dim=-1) if extras else None
         extr = extrinsic_matrix[:3, :]
         intr = intrinsic_params.reshape(-1)[:4] if intrinsic_params.numel() != 4 else intrinsic_params

@@ -79,3 +79,20 @@ def make_config(name: str, device="cpu", P: int | None = None, views: int | None
 def upstream_gradient(C: int, H: int, W: int, seed: int = 2, device="cpu") -> torch.Tensor:
     g = torch.Generator(device="cpu").manual_seed(seed)
     return torch.randn(C, H, W, generator=g).float().to(device)
+
+
+def target_images(n: int, H: int, W: int, seed: int = 2) -> torch.Tensor:
+    """``n`` fixed random target images [n,3,H,W] in [0,1] (the ground truth of the photometric loss,
+    SURVEY.md 8d: seed 2 = upstream-gradient / target images)."""
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return torch.rand(n, 3, H, W, generator=g).float()
+
+
+def extra_features(P: int, seed: int = 3) -> Dict[str, torch.Tensor]:
+    """Per-Gaussian feature columns of the cfg4 "render anything" sweep beside rgb and depth: unit
+    ``normals[P,3]`` and a 2-channel ``flow[P,2]`` (optical flow is representable only as
+    generic feature channels), passed to ``render_iter`` as keyword arguments => C = 3 + 1 + 3 + 2 = 9."""
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    n = torch.randn(P, 3, generator=g)
+    n = n / n.norm(dim=1, keepdim=True)
+    return {"normals": n.float().contiguous(), "flow": (torch.randn(P, 2, generator=g) * 2.0).float().contiguous()}

@@ -38,8 +38,8 @@ def test_clock_sampler_reports_only_the_timed_region():
 
 def test_reference_arm_prints_the_contract_line():
     env = dict(os.environ, RANK="0", WORLD_SIZE="1")
-    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
-                          "--warmup", "0", "--cpu-sample", "2000", "--config", "cfg1"], capture_output=True, text=True,
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "20",
+                          "--warmup", "5", "--cpu-sample", "2000", "--config", "cfg1"], capture_output=True, text=True,
                          env=env, timeout=600)
     assert out.returncode == 0, out.stderr[-2000:]
     lines = [ln for ln in out.stdout.splitlines() if ln.strip()]
@@ -47,9 +47,23 @@ def test_reference_arm_prints_the_contract_line():
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["higher_is_better"] is True and d["value"] > 0
     assert d["unit"] == "view-iterations/s" and d["n_gpus"] == 1 and d["gpu_launches"] == 0
+    # the arm reports the iterations it actually ran (bounded: <= 2 timed, <= 1 warm-up), not the request
+    assert d["steps"] == d["cpu_baseline"]["timed_iterations"] <= 2 and d["warmup"] <= 2
+    assert d["steps_requested"] == 20 and d["warmup_requested"] == 5
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and "sample" in d["cpu_baseline"]
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     # the other ranks of a torchrun launch exit 0 without work
     out1 = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2"],
                           capture_output=True, text=True, env=dict(os.environ, RANK="1", WORLD_SIZE="2"), timeout=120)
     assert out1.returncode == 0 and out1.stdout.strip() == ""
+
+
+def test_reference_arm_never_maps_the_product_library():
+    """`--impl reference` is the CPU oracle alone: libpointrix_b200.so must not be loaded by that process."""
+    code = ("import sys; sys.path.insert(0, %r); import bench; "
+            "r = bench.cpu_oracle_run('cfg1', 'train', 1, 0, 60.0, 500); assert r['value'] > 0; "
+            "r2 = bench.cpu_oracle_run('cfg1', 'render', 1, 0, 60.0, 500); assert r2['unit'] == 'Mpix/s'; "
+            "m = open('/proc/self/maps').read(); assert 'libpointrix_b200' not in m, 'product .so mapped'; "
+            "assert 'pointrix_b200' not in sys.modules") % ROOT
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]

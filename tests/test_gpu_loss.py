@@ -187,3 +187,21 @@ def test_render_then_loss_end_to_end(L):
     for k in grads[0]:
         assert grads[0][k].abs().sum().item() > 0, k
         assert l2_rel(grads[0][k], grads[1][k]) <= GRAD_TOL, k
+
+
+def test_loss_oracle_runs_on_cuda_tensors(L):
+    """bench.py times oracle/loss_oracle.py (the reference's torch-op formulation) on CUDA tensors beside the
+    fused kernels: its SSIM window must follow the image's device (`window.type_as(img1)`, loss.py:91-95)."""
+    from oracle import loss_oracle as LO
+
+    g = torch.Generator().manual_seed(5)
+    gt = torch.rand(1, 3, 70, 90, generator=g).cuda()
+    pred = (gt + 0.1 * torch.randn(gt.shape, generator=g).cuda()).clamp(0, 1)
+    p1 = pred.clone().requires_grad_()
+    d1 = LO.l1_ssim_loss(p1, gt, 0.2)
+    d1["loss"].backward()
+    p2 = pred.clone().requires_grad_()
+    d2 = L.l1_ssim_loss(p2, gt, 0.2)
+    d2["loss"].backward()
+    assert abs(d1["loss"].item() - d2["loss"].item()) <= VAL_TOL
+    assert rel_err(p2.grad, p1.grad) <= GRAD_TOL

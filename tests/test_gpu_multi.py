@@ -76,6 +76,28 @@ def _worker(rank, world, port, q):
             same_bits &= all(bool(torch.equal(a, allc[0])) for a in allc)
         worst["ranks_differ"] = 0.0 if same_bits else 1.0
         res[f"{kind}-{mode}"] = (worst, radii_ok, vis_ok)
+    # one backward per exchange: a second backward into a sink that still owes an exchange must raise
+    # (its buffers alias the first backward's .grad views), not silently corrupt gradients
+    guard_ok = True
+    for cls in (parallel.NvlsGradExchange, parallel.ShFactoredExchange):
+        ex = cls(P, dev, mode="p2p")
+        try:
+            run([rank, rank], ex)
+            guard_ok = False
+        except RuntimeError as e:
+            guard_ok &= "one backward per exchange" in str(e)
+        renderer.set_grad_sink(None)
+        dist.barrier()
+    res["guard"] = ({"second_backward_raises": 0.0 if guard_ok else 1.0}, True, True)
+    # average=True on raw (un-scaled) view losses == the reference batch: ndc grads carry 1/world too
+    params_u = {k: v.to(dev).requires_grad_() for k, v in sc.items()}
+    o_u = r.render_iter(H, W, cams["extrinsic_matrix"][rank].to(dev), cams["intrinsic_params"].to(dev),
+                        cams["camera_center"][rank].to(dev), **params_u)
+    (o_u["rendered_features_split"]["rgb"] * (dimg * world)).sum().backward()
+    parallel.allreduce_step([p.grad for p in params_u.values()], o_u["uv_points"].grad, o_u["radii"], world, average=True)
+    errs = {k: ((params_u[k].grad - p_all[k].grad).norm() / p_all[k].grad.norm().clamp_min(1e-30)).item() for k in p_all}
+    errs["ndc"] = ((o_u["uv_points"].grad - ndc_sum).norm() / ndc_sum.norm()).item()
+    res["nccl-average"] = (errs, bool(torch.equal(o_u["radii"], radii_max)), True)
     # the NCCL path of the same step
     p_mine, o_mine = run([rank], None)
     parallel.allreduce_step([p.grad for p in p_mine.values()], o_mine[0]["uv_points"].grad, o_mine[0]["radii"], world,

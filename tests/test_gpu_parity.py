@@ -247,7 +247,7 @@ def test_render_iter_extra_features_and_fallback(pb, ref):
     normals = torch.randn(P, 3, generator=g).cuda()
     flow = torch.randn(P, 2, generator=g).cuda()
     r = _renderer(pb, True, 3)
-    out = r.render_iter(H, W, E, intr, cc, **sc, normals=normals, flow=flow)
+    out = r.render_iter(H, W, E, intr, cc, **sc, normals=normals, extra_features={"flow": flow})
     sp = out["rendered_features_split"]
     assert list(sp) == ["rgb", "depth", "normals", "flow"]
     assert [v.shape[0] for v in sp.values()] == [3, 1, 3, 2]

@@ -110,8 +110,11 @@ def _worker(rank, world, port, q):
 
 
 def test_allreduce_step_gloo_world2():
-    """world_size ranks x 1 view == one reference batch of world_size views: parameter grads are
-    averaged, ndc grads summed, radii max-reduced, visibility = any."""
+    """world_size ranks x 1 view == one reference batch of world_size views.  average=True (each rank
+    back-propagated its un-scaled view loss): parameter grads become the mean AND every view's ndc grad
+    carries 1/world before the sum -- the reference's mean loss scales each view's ndc.grad by 1/B before
+    accumulate_viewspace_grad sums them (pointrix/model/loss.py:27-46, controller/gs.py:274-278); radii
+    max-reduced, visibility = any."""
     import numpy as np
     import torch.multiprocessing as mp
 
@@ -129,7 +132,8 @@ def test_allreduce_step_gloo_world2():
     for i in range(2):
         np.testing.assert_allclose(o0[i], (k0[i] + k1[i]) / 2, rtol=1e-6, atol=1e-6)
         np.testing.assert_allclose(o1[i], o0[i])
-    np.testing.assert_allclose(o0[2], k0[2] + k1[2], rtol=1e-6, atol=1e-6)
+    np.testing.assert_allclose(o0[2], (k0[2] + k1[2]) / 2, rtol=1e-6, atol=1e-6)
+    np.testing.assert_allclose(o1[2], o0[2])
     assert (o0[3] == np.maximum(k0[3], k1[3])).all() and (o0[4] == (o0[3] > 0)).all()
 
 

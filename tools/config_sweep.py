@@ -49,7 +49,7 @@ def run(name, mode):
     g = torch.Generator().manual_seed(7)
     extra = {}
     if mode == "fwd9":
-        extra = {"normals": torch.randn(P, 3, generator=g).to(dev), "flow": torch.randn(P, 2, generator=g).to(dev)}
+        extra = {"normals": torch.randn(P, 3, generator=g).to(dev), "extra_features": {"flow": torch.randn(P, 2, generator=g).to(dev)}}
     C = 9 if mode == "fwd9" else 3
     dimg = scene.upstream_gradient(C, H, W).to(dev)
     gt = torch.rand(1, 3, H, W, generator=g).to(dev)
