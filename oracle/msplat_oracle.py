@@ -331,7 +331,7 @@ def compute_sh(shs, view_dirs, visible: Optional[torch.Tensor] = None):
 def alpha_blending(
     uv, conic, opacity, feature, idx_sorted, tile_range, bg: float, W: int, H: int,
     ndc: Optional[torch.Tensor] = None, return_aux: bool = False, max_elems: int = 1 << 24,
-    dL_dout: Optional[torch.Tensor] = None,
+    dL_dout: Optional[torch.Tensor] = None, tile_mask: Optional[torch.Tensor] = None,
 ):
     """Front-to-back blend per 16x16 tile, vectorised over (tiles-in-chunk, 256
     pixels, list length).  Skip rules (alpha_blending.cu:80-94): power > 0;
@@ -348,6 +348,9 @@ def alpha_blending(
     [tiles, 256, list] intermediates of only ONE chunk are alive at a time; the returned image is
     detached.  Used by :func:`render_step` for the full-size CPU baseline (1 M Gaussians at 1080p would
     otherwise keep > 100 GB of autograd state).
+
+    ``tile_mask`` (bool [tiles], optional): blend only the marked tiles (the others stay background) --
+    the bounded SAMPLE of a full-size view that bench.py's ``cpu_baseline`` leg times.
     """
     C = feature.shape[1]
     gx, gy = (W + BLOCK - 1) // BLOCK, (H + BLOCK - 1) // BLOCK
@@ -358,6 +361,8 @@ def alpha_blending(
         uv = uv + (ndc - ndc.detach()) * scale
     tr = tile_range.to(torch.int64)
     counts = tr[:, 1] - tr[:, 0]
+    if tile_mask is not None:
+        counts = torch.where(tile_mask.to(dev), counts, torch.zeros_like(counts))
     out = torch.zeros(gy * BLOCK, gx * BLOCK, C, dtype=feature.dtype, device=dev)
     final_T = torch.ones(gy * BLOCK, gx * BLOCK, dtype=feature.dtype, device=dev)
     ncontrib = torch.zeros(gy * BLOCK, gx * BLOCK, dtype=torch.int32, device=dev)
@@ -463,6 +468,7 @@ def render_iter(
     height: int, width: int, extrinsic_matrix, intrinsic_params, camera_center,
     position, opacity, scaling, rotation, shs, sh_degree: int = 3, bg_color: float = 1.0,
     render_depth: bool = False, extra_features: Optional[Dict[str, torch.Tensor]] = None,
+    tile_mask: Optional[torch.Tensor] = None,
 ) -> Dict:
     direction = position - camera_center.reshape(1, 3)
     direction = direction / direction.norm(dim=1, keepdim=True)
@@ -484,7 +490,8 @@ def render_iter(
         feats.update(extra_features)
     feature = torch.cat(list(feats.values()), dim=-1)
     ndc = torch.zeros_like(uv, requires_grad=True)
-    img = alpha_blending(uv, conic, opacity, feature, idx_sorted, tile_range, bg_color, width, height, ndc)
+    img = alpha_blending(uv, conic, opacity, feature, idx_sorted, tile_range, bg_color, width, height, ndc,
+                         tile_mask=tile_mask)
     split, s = {}, 0
     for k, v in feats.items():
         split[k] = img[s : s + v.shape[-1]]
@@ -497,13 +504,15 @@ def render_iter(
 
 
 def render_step(height: int, width: int, extrinsic_matrix, intrinsic_params, camera_center,
-                position, opacity, scaling, rotation, shs, loss_fn, sh_degree: int = 3, bg_color: float = 1.0) -> Dict:
+                position, opacity, scaling, rotation, shs, loss_fn, sh_degree: int = 3, bg_color: float = 1.0,
+                tile_mask: Optional[torch.Tensor] = None) -> Dict:
     """One training iteration of :func:`render_iter` + ``loss_fn(rgb[3,H,W]) -> scalar`` + backward with
     bounded memory: the same math and the same gradients as ``loss_fn(render_iter(...)).backward()``, but
     the blend is differentiated chunk by chunk (``alpha_blending(dL_dout=...)``) behind a detached
     boundary, so full-size scenes fit the host.  Gradients land in ``.grad`` of the leaves passed in
     (Gaussian parameters and, when they require grad, the camera tensors); returns
-    ``{"rgb", "loss", "radii", "ndc_grad"}``.
+    ``{"rgb", "loss", "radii", "ndc_grad", "isect_total", "isect_blended"}``.  ``tile_mask``: see
+    :func:`alpha_blending` (a sample of the view's tiles; everything per-Gaussian still runs in full).
     """
     direction = position - camera_center.reshape(1, 3)
     direction = direction / direction.norm(dim=1, keepdim=True)
@@ -520,11 +529,13 @@ def render_step(height: int, width: int, extrinsic_matrix, intrinsic_params, cam
     # detached boundary: the blend sees leaves of its own
     b_uv, b_conic, b_op, b_feat = (t.detach().requires_grad_() for t in (uv, conic, opacity, rgb))
     with torch.no_grad():
-        img = alpha_blending(b_uv, b_conic, b_op, b_feat, idx_sorted, tile_range, bg_color, width, height)
+        img = alpha_blending(b_uv, b_conic, b_op, b_feat, idx_sorted, tile_range, bg_color, width, height,
+                             tile_mask=tile_mask)
     img.requires_grad_()
     loss = loss_fn(img)
     loss.backward()
-    alpha_blending(b_uv, b_conic, b_op, b_feat, idx_sorted, tile_range, bg_color, width, height, dL_dout=img.grad)
+    alpha_blending(b_uv, b_conic, b_op, b_feat, idx_sorted, tile_range, bg_color, width, height, dL_dout=img.grad,
+                   tile_mask=tile_mask)
     zero = torch.zeros_like
     g = [b_uv.grad if b_uv.grad is not None else zero(b_uv), b_conic.grad if b_conic.grad is not None else zero(b_conic),
          b_op.grad if b_op.grad is not None else zero(b_op), b_feat.grad if b_feat.grad is not None else zero(b_feat)]
@@ -532,4 +543,7 @@ def render_step(height: int, width: int, extrinsic_matrix, intrinsic_params, cam
     # the four boundary gradients back into the per-Gaussian graph
     torch.autograd.backward([uv, conic, opacity, rgb], g)
     scale = torch.tensor([0.5 * width, 0.5 * height], dtype=uv.dtype)
-    return {"rgb": img.detach(), "loss": loss.detach(), "radii": radius, "ndc_grad": g[0] * scale}
+    per_tile = (tile_range[:, 1] - tile_range[:, 0]).to(torch.int64)
+    return {"rgb": img.detach(), "loss": loss.detach(), "radii": radius, "ndc_grad": g[0] * scale,
+            "isect_total": int(per_tile.sum()),
+            "isect_blended": int(per_tile.sum() if tile_mask is None else per_tile[tile_mask].sum())}

@@ -4,8 +4,13 @@
 // The reference sorts all N tile intersections by the 64-bit key tile<<32|depth (torch.sort, 8 radix
 // passes over N pairs + a gather).  The same order -- ascending (tile, depth bits), ties in
 // emission order = ascending Gaussian id -- is produced here with far less traffic:
-//   1. stable LSD radix sort of the P Gaussians by depth bits (4 passes over P, P << N);
-//   2. inclusive prefix sum of tiles-touched in that order (single pass, decoupled look-back);
+//   1. order-preserving compaction of the VISIBLE Gaussians (radius > 0 and at least one tile), then a
+//      stable LSD radix sort of those M <= P (depth bits, id) pairs (4 passes over M, M << N).  The
+//      digit histogram of pass k+1 is accumulated by the scatter of pass k (one RED per pair), that of
+//      pass 0 by the compaction, so a pass is two kernels (scan over chunks, scatter) instead of three;
+//   2. the last pass also sums the tiles-touched of every 1024 sorted Gaussians; the key emission
+//      turns those chunk sums into its write offsets itself (no separate prefix-sum kernel, no offsets
+//      array) and publishes the intersection count;
 //   3. key emission in depth order: (tile id, Gaussian id) pairs, warp-cooperative so every store
 //      is coalesced and big Gaussians do not serialise one thread;
 //   4. stable radix sort of the N pairs by TILE ID ONLY (ceil(log2 tiles)/8 = 2 passes at 1080p):
@@ -19,168 +24,219 @@
 
 namespace pxb {
 
-// ---------------------------------------------------------------------------
-// single-pass inclusive scan (decoupled look-back, warp-parallel), int32, with an optional gather
-// ---------------------------------------------------------------------------
-constexpr int kScanThreads = 256;
-constexpr int kScanItems = 8;
-constexpr int kScanTile = kScanThreads * kScanItems;
-#define kFlagAgg (1ull << 32)
-#define kFlagPrefix (2ull << 32)
+constexpr int kRadix = 256;
 
-// out[i] = sum_{j<=i} cnt(order[j]),  cnt(g) = radius[g] > 0 ? tiles[g] : 0
-__global__ void __launch_bounds__(kScanThreads)
-scan_kernel(int P, const int* __restrict__ tiles, const int* __restrict__ radius, const unsigned int* __restrict__ order,
-            int* __restrict__ out, int* __restrict__ total, int* __restrict__ total_host, unsigned long long* status,
-            unsigned int* ticket) {
-    __shared__ int s_warp[kScanThreads / 32];
-    __shared__ int s_tile, s_excl;
-    if (threadIdx.x == 0) s_tile = (int)atomicAdd(ticket, 1u);
-    __syncthreads();
-    const int tile = s_tile;
-    const int base = tile * kScanTile + threadIdx.x * kScanItems;
-    int v[kScanItems];
-    int sum = 0;
+__device__ __forceinline__ unsigned int warp_sum_u32(unsigned int v) {
 #pragma unroll
-    for (int k = 0; k < kScanItems; k++) {
-        v[k] = 0;
-        if (base + k < P) {
-            const int g = order ? (int)order[base + k] : base + k;
-            v[k] = (radius == nullptr || radius[g] > 0) ? tiles[g] : 0;
-        }
-        sum += v[k];
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// ---------------------------------------------------------------------------
+// order-preserving compaction of the visible Gaussians (+ digit histogram of radix pass 0)
+//   visible(g) = radius[g] > 0 && tiles[g] > 0      (tiles: the count the emission will use)
+// Two kernels without any inter-CTA dependency: per-chunk counts (skipped when the fused forward has
+// already accumulated them), then every CTA sums the counts of the chunks before it (<= P/1024 words).
+// ---------------------------------------------------------------------------
+constexpr int kCompThreads = 256;
+constexpr int kCompChunk = 1024;  // Gaussians per CTA, 4 consecutive ids per thread
+
+__global__ void __launch_bounds__(kCompThreads)
+count_visible_kernel(int P, const int* __restrict__ radius, const int* __restrict__ tiles,
+                     unsigned int* __restrict__ vis_cnt) {
+    pdl_wait();
+    __shared__ unsigned int s_w[kCompThreads / 32];
+    const int i0 = blockIdx.x * kCompChunk + threadIdx.x * 4;
+    unsigned int c = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+        if (i0 + k < P) c += (radius[i0 + k] > 0 && tiles[i0 + k] > 0) ? 1u : 0u;
+    c = warp_sum_u32(c);
+    if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned int t = 0;
+#pragma unroll
+        for (int w = 0; w < kCompThreads / 32; w++) t += s_w[w];
+        vis_cnt[blockIdx.x] = t;
     }
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    int incl = sum;
+}
+
+// keys[j] = depth bits, vals[j] = id of the j-th visible Gaussian (ascending id); *m_dev = their number;
+// counts0[digit][chunk] += 1 for the lowest radix digit (chunk = j >> log_chunk, row pitch T)
+__global__ void __launch_bounds__(kCompThreads)
+compact_kernel(int P, const float* __restrict__ depth, const int* __restrict__ radius, const int* __restrict__ tiles,
+               const unsigned int* __restrict__ vis_cnt, unsigned int* __restrict__ keys, unsigned int* __restrict__ vals,
+               int* __restrict__ m_dev, unsigned int* __restrict__ counts0, int T, int log_chunk) {
+    pdl_wait();
+    __shared__ unsigned int s_w[kCompThreads / 32], s_v[kCompThreads / 32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    unsigned int part = 0;
+    for (int c = tid; c < (int)blockIdx.x; c += kCompThreads) part += vis_cnt[c];
+    part = warp_sum_u32(part);
+    const int i0 = blockIdx.x * kCompChunk + tid * 4;
+    bool vis[4];
+    unsigned int n = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        vis[k] = (i0 + k < P) && radius[i0 + k] > 0 && tiles[i0 + k] > 0;
+        n += vis[k] ? 1u : 0u;
+    }
+    unsigned int incl = n;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-        const int n = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += n;
+        const unsigned int x = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += x;
     }
-    if (lane == 31) s_warp[warp] = incl;
+    if (lane == 0) s_w[warp] = part;
+    if (lane == 31) s_v[warp] = incl;
     __syncthreads();
-    int warp_off = 0, block_sum = 0;
+    unsigned int base = 0, woff = 0, total = 0;
 #pragma unroll
-    for (int w = 0; w < kScanThreads / 32; w++) {
-        const int s = s_warp[w];
-        if (w < warp) warp_off += s;
-        block_sum += s;
+    for (int w = 0; w < kCompThreads / 32; w++) {
+        base += s_w[w];
+        if (w < warp) woff += s_v[w];
+        total += s_v[w];
     }
-    if (warp == 0) {
-        // warp-parallel decoupled look-back: 32 predecessors per probe
-        volatile unsigned long long* st = status;
-        if (lane == 0) st[tile] = (tile == 0 ? kFlagPrefix : kFlagAgg) | (unsigned int)block_sum;
-        int excl = 0;
-        int t_base = tile - 1;
-        while (t_base >= 0) {
-            const int idx = t_base - lane;
-            const unsigned long long sv = (idx >= 0) ? st[idx] : kFlagPrefix;
-            const unsigned int flag = (unsigned int)(sv >> 32);
-            const unsigned int zero = __ballot_sync(0xffffffffu, flag == 0);
-            const unsigned int pref = __ballot_sync(0xffffffffu, flag == 2);
-            const int first = pref ? (__ffs(pref) - 1) : 32;  // nearest tile holding an inclusive prefix
-            const unsigned int need = (first < 32) ? ((2u << first) - 1u) : 0xffffffffu;
-            if (zero & need) continue;  // some needed predecessor not published yet
-            int v_ = (lane <= first) ? (int)(unsigned int)sv : 0;
+    unsigned int pos = base + woff + incl - n;
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) v_ += __shfl_xor_sync(0xffffffffu, v_, o);
-            excl += v_;
-            if (first < 32) break;
-            t_base -= 32;
+    for (int k = 0; k < 4; k++)
+        if (vis[k]) {
+            const unsigned int key = __float_as_uint(depth[i0 + k]);
+            keys[pos] = key;
+            vals[pos] = (unsigned int)(i0 + k);
+            atomicAdd(&counts0[(size_t)(key & (kRadix - 1)) * T + (pos >> log_chunk)], 1u);
+            pos++;
         }
-        if (lane == 0) {
-            if (tile > 0) st[tile] = kFlagPrefix | (unsigned int)(excl + block_sum);
-            s_excl = excl;
-            if ((tile + 1) * kScanTile >= P) {
-                *total = excl + block_sum;
-                if (total_host) {  // pinned host word the caller polls (no memcpy in the stream)
-                    *reinterpret_cast<volatile int*>(total_host) = excl + block_sum;
-                    __threadfence_system();
-                }
-            }
-        }
-    }
-    __syncthreads();
-    int run = s_excl + warp_off + (incl - sum);
-#pragma unroll
-    for (int k = 0; k < kScanItems; k++) {
-        run += v[k];
-        if (base + k < P) out[base + k] = run;
-    }
+    if (blockIdx.x == gridDim.x - 1 && tid == 0) *m_dev = (int)(base + total);
 }
 
-// depth bits + identity permutation: the input of the Gaussian-order sort
-__global__ void init_depth_keys_kernel(int P, const float* __restrict__ depth, unsigned int* __restrict__ keys,
-                                       unsigned int* __restrict__ vals) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= P) return;
-    keys[i] = __float_as_uint(depth[i]);
-    vals[i] = (unsigned int)i;
+// *total = sum of the chunk sums (the intersection count N); operator path only -- the fused path lets the
+// key emission publish it
+__global__ void __launch_bounds__(256)
+sum_chunks_kernel(const int* __restrict__ m_dev, const int* __restrict__ chunk_tiles, int* __restrict__ total) {
+    pdl_wait();
+    __shared__ unsigned int s_w[8];
+    const int nchunks = (*m_dev + kCompChunk - 1) / kCompChunk;
+    unsigned int v = 0;
+    for (int c = threadIdx.x; c < nchunks; c += 256) v += (unsigned int)chunk_tiles[c];
+    v = warp_sum_u32(v);
+    if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned int t = 0;
+        for (int w = 0; w < 8; w++) t += s_w[w];
+        *total = (int)t;
+    }
 }
 
 // ---------------------------------------------------------------------------
-// key emission: sorted position i holds Gaussian g = order[i]; its tile ids go to
-// [offs_incl[i] - cnt, offs_incl[i])
+// key emission: sorted position i (< M) holds Gaussian g = order[i]; its cnt(g) tile ids go to
+// [off, off + cnt) with off = sum of cnt over the sorted positions before i.  A CTA owns 1024 sorted
+// positions: the sums of the chunks before it (accumulated by the last depth pass) give its base, a
+// CTA-wide scan per round of 256 the rest.  Block 0 publishes N = sum of all chunks.
 // ---------------------------------------------------------------------------
 constexpr int kEmitThreads = 256;
 
 __global__ void __launch_bounds__(kEmitThreads)
-emit_keys_kernel(int P, const float* __restrict__ uv, int uv_stride, const int* __restrict__ radius,
-                 const int* __restrict__ tiles, const unsigned int* __restrict__ order,
-                 const int* __restrict__ offs_incl, int gx, int gy, int tight, long long N_cap,
-                 const int* __restrict__ n_dev, unsigned int* __restrict__ keys, unsigned int* __restrict__ vals) {
-    const long long N = n_dev ? min((long long)*n_dev, N_cap) : N_cap;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    const int lane = threadIdx.x & 31;
-    int x0 = 0, y0 = 0, w = 1, cnt = 0, off = 0, g = 0;
-    if (i < P) {
-        g = (int)order[i];
-        const int r = radius[g];
-        if (r > 0) {
-            int x1, y1;
-            const float* rg = uv + (size_t)g * uv_stride;
-            if (tight)  // uv is the packed blend record {u,v,A,B,C,op,...}: the fused path's rectangle
-                tight_tile_rect(rg[0], rg[1], r, rg[2], rg[3], rg[4], rg[5], gx, gy, x0, y0, x1, y1);
-            else
-                tile_rect(rg[0], rg[1], r, gx, gy, x0, y0, x1, y1);
-            w = max(x1 - x0, 1);
-            cnt = tiles[g];  // == w * (y1 - y0) (ewa_project.cu:81); the scan used the same count
-            off = offs_incl[i] - cnt;
+emit_keys_kernel(const int* __restrict__ m_dev, const float* __restrict__ uv, int uv_stride, const int* __restrict__ radius,
+                 const int* __restrict__ tiles, const int2* __restrict__ rect, const unsigned int* __restrict__ order,
+                 const int* __restrict__ chunk_tiles, int gx, int gy, int tight, long long N_cap, int* __restrict__ n_dev,
+                 int* __restrict__ n_host, unsigned int* __restrict__ keys, unsigned int* __restrict__ vals) {
+    pdl_wait();
+    __shared__ unsigned int s_a[kEmitThreads / 32], s_b[kEmitThreads / 32];
+    const int M = *m_dev;
+    const int nchunks = (M + kCompChunk - 1) / kCompChunk;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if ((int)blockIdx.x >= nchunks && blockIdx.x != 0) return;
+    unsigned int before = 0, all = 0;
+    for (int c = tid; c < nchunks; c += kEmitThreads) {
+        const unsigned int v = (unsigned int)chunk_tiles[c];
+        all += v;
+        if (c < (int)blockIdx.x) before += v;
+    }
+    before = warp_sum_u32(before);
+    all = warp_sum_u32(all);
+    if (lane == 0) { s_a[warp] = before; s_b[warp] = all; }
+    __syncthreads();
+    unsigned int run = 0, total_all = 0;
+#pragma unroll
+    for (int w = 0; w < kEmitThreads / 32; w++) { run += s_a[w]; total_all += s_b[w]; }
+    if (blockIdx.x == 0 && tid == 0) {
+        *n_dev = (int)total_all;
+        if (n_host) {  // pinned host word the caller polls (no memcpy in the stream)
+            *reinterpret_cast<volatile int*>(n_host) = (int)total_all;
+            __threadfence_system();
         }
     }
-    // warp-cooperative expansion: slot s of the warp's cnt-sum belongs to the lane whose inclusive
-    // prefix first exceeds s
-    int incl = cnt;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const int n = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += n;
-    }
-    const int total = __shfl_sync(0xffffffffu, incl, 31);
-    const int excl = incl - cnt;
-    for (int s = lane; s < ((total + 31) & ~31); s += 32) {
-        int lo = 0;  // binary search over the 32 inclusive prefixes (held one per lane)
-#pragma unroll
-        for (int step = 16; step > 0; step >>= 1) {
-            const int probe = __shfl_sync(0xffffffffu, incl, lo + step - 1);
-            if (probe <= s) lo += step;
-        }
-        const int src = min(lo, 31);
-        const int e_src = __shfl_sync(0xffffffffu, excl, src);
-        const int x0s = __shfl_sync(0xffffffffu, x0, src);
-        const int y0s = __shfl_sync(0xffffffffu, y0, src);
-        const int ws = __shfl_sync(0xffffffffu, w, src);
-        const int offs = __shfl_sync(0xffffffffu, off, src);
-        const int gs = __shfl_sync(0xffffffffu, g, src);
-        if (s < total) {
-            const int local = s - e_src;
-            const int row = local / ws, col = local - row * ws;
-            const long long pos = (long long)offs + local;
-            if (pos >= 0 && pos < N) {
-                keys[pos] = (unsigned int)((y0s + row) * gx + (x0s + col));
-                vals[pos] = (unsigned int)gs;
+    if ((int)blockIdx.x >= nchunks) return;
+    __syncthreads();
+    for (int round = 0; round < kCompChunk / kEmitThreads; round++) {
+        const int i = blockIdx.x * kCompChunk + round * kEmitThreads + tid;
+        int x0 = 0, y0 = 0, w = 1, cnt = 0, g = 0;
+        if (i < M) {
+            g = (int)order[i];
+            if (rect != nullptr) {  // the fused forward's own rectangle: {x0 | y0 << 16, w | h << 16}
+                const int2 r = rect[g];
+                x0 = r.x & 0xffff; y0 = r.x >> 16;
+                w = max(r.y & 0xffff, 1);
+                cnt = (r.y & 0xffff) * (r.y >> 16);
+            } else {
+                int x1, y1;
+                const float* rg = uv + (size_t)g * uv_stride;
+                if (tight)  // uv is the packed blend record {u,v,A,B,C,op,...}
+                    tight_tile_rect(rg[0], rg[1], radius[g], rg[2], rg[3], rg[4], rg[5], gx, gy, x0, y0, x1, y1);
+                else
+                    tile_rect(rg[0], rg[1], radius[g], gx, gy, x0, y0, x1, y1);
+                w = max(x1 - x0, 1);
+                cnt = tiles[g];  // == w * (y1 - y0) (ewa_project.cu:81); the chunk sums used the same count
             }
         }
+        // warp scan of the counts, then the warps' offsets inside this round
+        int incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int n = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += n;
+        }
+        const int total = __shfl_sync(0xffffffffu, incl, 31);
+        if (lane == 31) s_a[warp] = (unsigned int)incl;
+        __syncthreads();
+        unsigned int woff = 0, round_total = 0;
+#pragma unroll
+        for (int k = 0; k < kEmitThreads / 32; k++) {
+            if (k < warp) woff += s_a[k];
+            round_total += s_a[k];
+        }
+        const int excl = incl - cnt;
+        const long long wbase = (long long)run + woff;  // first slot of this warp's Gaussians
+        // warp-cooperative expansion: slot s of the warp's cnt-sum belongs to the lane whose inclusive
+        // prefix first exceeds s
+        for (int s = lane; s < ((total + 31) & ~31); s += 32) {
+            int lo = 0;  // binary search over the 32 inclusive prefixes (held one per lane)
+#pragma unroll
+            for (int step = 16; step > 0; step >>= 1) {
+                const int probe = __shfl_sync(0xffffffffu, incl, lo + step - 1);
+                if (probe <= s) lo += step;
+            }
+            const int src = min(lo, 31);
+            const int e_src = __shfl_sync(0xffffffffu, excl, src);
+            const int x0s = __shfl_sync(0xffffffffu, x0, src);
+            const int y0s = __shfl_sync(0xffffffffu, y0, src);
+            const int ws = __shfl_sync(0xffffffffu, w, src);
+            const int gs = __shfl_sync(0xffffffffu, g, src);
+            if (s < total) {
+                const int local = s - e_src;
+                const int row = local / ws, col = local - row * ws;
+                const long long pos = wbase + s;
+                if (pos < N_cap) {
+                    keys[pos] = (unsigned int)((y0s + row) * gx + (x0s + col));
+                    vals[pos] = (unsigned int)gs;
+                }
+            }
+        }
+        run += round_total;
+        __syncthreads();  // s_a is rewritten by the next round
     }
 }
 
@@ -197,10 +253,11 @@ emit_keys_kernel(int P, const float* __restrict__ uv, int uv_stride, const int* 
 // per pass (4 B/pair) removes every inter-CTA dependency.
 // ---------------------------------------------------------------------------
 constexpr int kRsThreads = 256;
-constexpr int kRsItems = 16;
-constexpr int kRsTile = kRsThreads * kRsItems;  // 4096 pairs per CTA
-constexpr int kRadix = 256;
 constexpr int kMaxPasses = 4;
+// pairs per thread: 16 (4096 per CTA) for the N-level tile sort; 8 (2048 per CTA) for the P-level depth
+// sort, whose <= P/2048 CTAs are all resident at once -- smaller chunks halve the serial ranking chain
+constexpr int kItemsN = 16;
+constexpr int kItemsP = 8;
 
 // digit layout of one radix sort: pass p ranks bits [shift[p], shift[p]+bits[p]) (bits <= 8)
 struct RsDigits {
@@ -223,26 +280,28 @@ static RsDigits make_digits(int total_bits) {
     return d;
 }
 
-template <int NBITS>
+template <int NBITS, int ITEMS>
 __global__ void __launch_bounds__(kRsThreads)
 rs_tile_hist_kernel(const unsigned int* __restrict__ keys, int N_cap, const int* __restrict__ n_dev, int shift, int T,
                     unsigned int* __restrict__ counts /*[2^NBITS][T]*/) {
+    pdl_wait();
     constexpr int NB = 1 << NBITS;
     constexpr int NW = kRsThreads / 32;
+    constexpr int TILE = kRsThreads * ITEMS;
     __shared__ unsigned int h[NW][NB];  // warp-private: 8x less contention on skewed digits
     const int N = n_dev ? min(*n_dev, N_cap) : N_cap;
     const int tid = threadIdx.x, warp = tid >> 5;
     for (int k = tid; k < NW * NB; k += kRsThreads) (&h[0][0])[k] = 0;
     __syncthreads();
-    const long long base = (long long)blockIdx.x * kRsTile;
-    unsigned int key[kRsItems];
+    const long long base = (long long)blockIdx.x * TILE;
+    unsigned int key[ITEMS];
 #pragma unroll
-    for (int k = 0; k < kRsItems; k++) {
+    for (int k = 0; k < ITEMS; k++) {
         const long long p = base + k * kRsThreads + tid;
         key[k] = p < N ? keys[p] : 0u;
     }
 #pragma unroll
-    for (int k = 0; k < kRsItems; k++)
+    for (int k = 0; k < ITEMS; k++)
         if (base + k * kRsThreads + tid < N) atomicAdd(&h[warp][(key[k] >> shift) & (NB - 1)], 1u);
     __syncthreads();
     for (int k = tid; k < NB; k += kRsThreads) {
@@ -256,6 +315,7 @@ rs_tile_hist_kernel(const unsigned int* __restrict__ keys, int N_cap, const int*
 // one CTA per digit: exclusive scan of counts[digit][0..T) in place, totals[digit] = row sum
 __global__ void __launch_bounds__(1024) rs_tile_scan_kernel(unsigned int* __restrict__ counts, int T,
                                                             unsigned int* __restrict__ totals) {
+    pdl_wait();
     __shared__ unsigned int s_warp[32];
     __shared__ unsigned int s_total;
     unsigned int* row = counts + (size_t)blockIdx.x * T;
@@ -291,31 +351,48 @@ __global__ void __launch_bounds__(1024) rs_tile_scan_kernel(unsigned int* __rest
     if (tid == 0) totals[blockIdx.x] = carry;
 }
 
+// what a scatter pass accumulates for its successor while it writes out (one RED per pair)
+enum RsNext {
+    kNextNone = 0,
+    kNextHist = 1,   // digit histogram of the NEXT pass: next_counts[digit][dst / TILE] += 1
+    kNextTiles = 2,  // last depth pass: chunk_tiles[dst / 1024] += tiles[value]
+};
+struct RsAux {
+    unsigned int* next_counts;  // kNextHist
+    int next_shift;
+    const int* tiles;           // kNextTiles
+    int* chunk_tiles;
+};
+
+template <int ITEMS>
 struct RsSmem {
-    uint2 pairs[kRsTile];  // (key, value) exchange buffer; its first 16 KB double as the match masks
+    uint2 pairs[kRsThreads * ITEMS];  // (key, value) exchange buffer; its first 16 KB double as the match masks
     unsigned int warp_hist[kRsThreads / 32][kRadix];
     unsigned int digit_start[kRadix];
     int gbase[kRadix];
     unsigned int warp_sums[kRadix / 32];
 };
 
-// FULL: the tile holds exactly kRsTile pairs (every tile but the last) -- no bounds predicates
-template <int NBITS, bool FULL>
-__device__ __forceinline__ void rs_scatter_tile(RsSmem& sm, const unsigned int* __restrict__ keys_in,
+// FULL: the tile holds exactly TILE pairs (every tile but the last) -- no bounds predicates
+template <int NBITS, int ITEMS, int NEXT, bool FULL>
+__device__ __forceinline__ void rs_scatter_tile(RsSmem<ITEMS>& sm, const unsigned int* __restrict__ keys_in,
                                                 const unsigned int* __restrict__ vals_in,
                                                 unsigned int* __restrict__ keys_out, unsigned int* __restrict__ vals_out,
                                                 long long tile_base, int tile_n, int shift, int T, int tile,
                                                 const unsigned int* __restrict__ counts_excl,
-                                                const unsigned int* __restrict__ totals) {
+                                                const unsigned int* __restrict__ totals, const RsAux& aux) {
     constexpr int NB = 1 << NBITS;
     constexpr unsigned int kDigitMask = NB - 1u;
+    constexpr int LOG_TILE = (ITEMS == 16) ? 12 : 11;
+    static_assert(kRsThreads * ITEMS == (1 << LOG_TILE), "tile size");
+    static_assert(sizeof(uint2) * kRsThreads * ITEMS >= (kRsThreads / 32) * 2 * kRadix * 4, "mask buffers alias pairs[]");
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     // warp-striped load: item k of lane l in warp w sits at w*32*IPT + k*32 + l
-    unsigned int key[kRsItems];
-    unsigned int val[kRsItems];
-    const int wbase = warp * 32 * kRsItems + lane;
+    unsigned int key[ITEMS];
+    unsigned int val[ITEMS];
+    const int wbase = warp * 32 * ITEMS + lane;
 #pragma unroll
-    for (int k = 0; k < kRsItems; k++) {
+    for (int k = 0; k < ITEMS; k++) {
         const int p = wbase + k * 32;
         if (FULL || p < tile_n) {
             key[k] = keys_in[tile_base + p];
@@ -339,9 +416,9 @@ __device__ __forceinline__ void rs_scatter_tile(RsSmem& sm, const unsigned int* 
     unsigned int* mk = reinterpret_cast<unsigned int*>(sm.pairs) + warp * (2 * kRadix);
     for (int k = lane; k < 2 * NB; k += 32) mk[(k / NB) * kRadix + (k % NB)] = 0;
     __syncwarp();
-    unsigned int rank2[kRsItems / 2];  // two 16-bit ranks per register (rank < kRsTile = 4096)
+    unsigned int rank2[ITEMS / 2];  // two 16-bit ranks per register (rank < TILE <= 4096)
 #pragma unroll
-    for (int k = 0; k < kRsItems; k++) {
+    for (int k = 0; k < ITEMS; k++) {
         const bool valid = FULL || (wbase + k * 32) < tile_n;
         const unsigned int d = (key[k] >> shift) & kDigitMask;
         unsigned int* m = mk + (k & 1) * kRadix;
@@ -387,7 +464,7 @@ __device__ __forceinline__ void rs_scatter_tile(RsSmem& sm, const unsigned int* 
     __syncthreads();
     // scatter into tile-local sorted order
 #pragma unroll
-    for (int k = 0; k < kRsItems; k++) {
+    for (int k = 0; k < ITEMS; k++) {
         if (FULL || (wbase + k * 32) < tile_n) {
             const unsigned int d = (key[k] >> shift) & kDigitMask;
             const unsigned int pos = sm.digit_start[d] + sm.warp_hist[warp][d] + ((rank2[k >> 1] >> (16 * (k & 1))) & 0xffffu);
@@ -397,35 +474,40 @@ __device__ __forceinline__ void rs_scatter_tile(RsSmem& sm, const unsigned int* 
     __syncthreads();
     // coalesced write-out: consecutive sorted positions of one digit are consecutive in global memory
 #pragma unroll
-    for (int k = 0; k < kRsItems; k++) {
+    for (int k = 0; k < ITEMS; k++) {
         const int p = k * kRsThreads + tid;
         if (FULL || p < tile_n) {
             const uint2 kv = sm.pairs[p];
             const int dst = sm.gbase[(kv.x >> shift) & kDigitMask] + p;
             keys_out[dst] = kv.x;
             vals_out[dst] = kv.y;
+            if (NEXT == kNextHist)
+                atomicAdd(&aux.next_counts[(size_t)((kv.x >> aux.next_shift) & (kRadix - 1)) * T + (dst >> LOG_TILE)], 1u);
+            if (NEXT == kNextTiles) atomicAdd(&aux.chunk_tiles[dst >> 10], aux.tiles[kv.y]);
         }
     }
 }
 
-template <int NBITS>
+template <int NBITS, int ITEMS, int NEXT>
 __global__ void __launch_bounds__(kRsThreads, 3)
 rs_scatter_kernel(const unsigned int* __restrict__ keys_in, const unsigned int* __restrict__ vals_in,
                   unsigned int* __restrict__ keys_out, unsigned int* __restrict__ vals_out, int N_cap,
                   const int* __restrict__ n_dev, int shift, int T, const unsigned int* __restrict__ counts_excl,
-                  const unsigned int* __restrict__ totals) {
+                  const unsigned int* __restrict__ totals, RsAux aux) {
+    pdl_wait();
+    constexpr int TILE = kRsThreads * ITEMS;
     const int N = n_dev ? min(*n_dev, N_cap) : N_cap;
-    __shared__ RsSmem sm;
+    __shared__ RsSmem<ITEMS> sm;
     const int tile = blockIdx.x;
-    const long long tile_base = (long long)tile * kRsTile;
+    const long long tile_base = (long long)tile * TILE;
     if (tile_base >= N) return;  // capacity-sized grid: surplus CTAs leave
     for (int k = threadIdx.x; k < (kRsThreads / 32) * kRadix; k += kRsThreads) (&sm.warp_hist[0][0])[k] = 0;
     __syncthreads();
-    const int tile_n = (int)min((long long)kRsTile, (long long)N - tile_base);
-    if (tile_n == kRsTile)
-        rs_scatter_tile<NBITS, true>(sm, keys_in, vals_in, keys_out, vals_out, tile_base, tile_n, shift, T, tile, counts_excl, totals);
+    const int tile_n = (int)min((long long)TILE, (long long)N - tile_base);
+    if (tile_n == TILE)
+        rs_scatter_tile<NBITS, ITEMS, NEXT, true>(sm, keys_in, vals_in, keys_out, vals_out, tile_base, tile_n, shift, T, tile, counts_excl, totals, aux);
     else
-        rs_scatter_tile<NBITS, false>(sm, keys_in, vals_in, keys_out, vals_out, tile_base, tile_n, shift, T, tile, counts_excl, totals);
+        rs_scatter_tile<NBITS, ITEMS, NEXT, false>(sm, keys_in, vals_in, keys_out, vals_out, tile_base, tile_n, shift, T, tile, counts_excl, totals, aux);
 }
 
 // ---------------------------------------------------------------------------
@@ -434,6 +516,7 @@ rs_scatter_kernel(const unsigned int* __restrict__ keys_in, const unsigned int* 
 __global__ void __launch_bounds__(256)
 tile_range_kernel(int N_cap, const int* __restrict__ n_dev, const unsigned int* __restrict__ tile_sorted,
                   int num_tiles, int2* __restrict__ tile_range) {
+    pdl_wait();
     const int N = n_dev ? min(*n_dev, N_cap) : N_cap;
     // four consecutive entries per thread (one 16-byte load) plus the entry before them
     const int i0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
@@ -481,48 +564,47 @@ static inline int tile_passes(int num_tiles) { return (tile_bits(num_tiles) + 7)
 
 // P-sized workspace: survives from pxb_bin_prepare to pxb_sort_gaussian
 struct WsP {
-    unsigned char* ctl; size_t ctl_bytes;          // zeroed per call
-    unsigned long long* scan_status; unsigned int* scan_ticket;
-    unsigned int* totals; unsigned int* counts;
-    unsigned int* keys[2]; unsigned int* vals[2];  // depth-sort ping-pong; result in keys[0]/vals[0] (4 passes)
-    int* offsets;
+    unsigned char* ctl; size_t ctl_bytes;            // zeroed per call (one memset)
+    unsigned int* vis_cnt;                           // visible Gaussians per 1024-id chunk
+    int* chunk_tiles;                                // tiles touched per 1024 depth-sorted Gaussians
+    unsigned int* counts[kMaxPasses];                // [256][T] per depth pass (accumulated by REDs)
+    int* m_dev;                                      // number of visible Gaussians
+    unsigned int* totals;                            // [256], rewritten by every scan
+    unsigned int* keys[2]; unsigned int* vals[2];    // depth-sort ping-pong; result in keys[0]/vals[0] (4 passes)
+    int T;                                           // chunks of kItemsP * 256 pairs
     size_t total;
 };
 static WsP carve_p(void* ws, int P) {
     WsP b;
-    const size_t scan_tiles = (size_t)(P + kScanTile - 1) / kScanTile + 1;
-    const size_t rs_tiles = (size_t)(P + kRsTile - 1) / kRsTile + 1;
+    const size_t chunks = (size_t)(P + kCompChunk - 1) / kCompChunk + 1;
+    b.T = (P + kRsThreads * kItemsP - 1) / (kRsThreads * kItemsP);
     size_t o = 0;
     unsigned char* base = (unsigned char*)ws;
     b.ctl = base;
-    b.scan_status = (unsigned long long*)(base + o); o += align_up(scan_tiles * 8, 256);
-    b.scan_ticket = (unsigned int*)(base + o); o += 256;
+    b.m_dev = (int*)(base + o); o += 256;
+    b.vis_cnt = (unsigned int*)(base + o); o += align_up(chunks * 4, 256);
+    b.chunk_tiles = (int*)(base + o); o += align_up(chunks * 4, 256);
+    for (int p = 0; p < kMaxPasses; p++) { b.counts[p] = (unsigned int*)(base + o); o += align_up((size_t)kRadix * b.T * 4, 256); }
     b.ctl_bytes = o;
     b.totals = (unsigned int*)(base + o); o += align_up((size_t)kRadix * 4, 256);
-    b.counts = (unsigned int*)(base + o); o += align_up(rs_tiles * kRadix * 4, 256);
     for (int k = 0; k < 2; k++) {
         b.keys[k] = (unsigned int*)(base + o); o += align_up((size_t)P * 4, 256);
         b.vals[k] = (unsigned int*)(base + o); o += align_up((size_t)P * 4, 256);
     }
-    b.offsets = (int*)(base + o); o += align_up((size_t)P * 4, 256);
     b.total = o;
     return b;
 }
 // N-sized workspace of pxb_sort_gaussian
 struct WsN {
-    unsigned char* ctl; size_t ctl_bytes;
     unsigned int* totals; unsigned int* counts;
     unsigned int* keys[2]; unsigned int* vals_tmp;
     size_t total;
 };
 static WsN carve_n(void* ws, long long Ncap, int num_tiles) {
     WsN b;
-    const int passes = tile_passes(num_tiles);
-    const size_t rs_tiles = (size_t)((Ncap + kRsTile - 1) / kRsTile) + 1;
+    const size_t rs_tiles = (size_t)((Ncap + kRsThreads * kItemsN - 1) / (kRsThreads * kItemsN)) + 1;
     size_t o = 0;
     unsigned char* base = (unsigned char*)ws;
-    b.ctl = base;
-    b.ctl_bytes = 0;
     b.totals = (unsigned int*)(base + o); o += align_up((size_t)kRadix * 4, 256);
     b.counts = (unsigned int*)(base + o); o += align_up(rs_tiles * kRadix * 4, 256);
     for (int k = 0; k < 2; k++) { b.keys[k] = (unsigned int*)(base + o); o += align_up((size_t)Ncap * 4, 256); }
@@ -531,30 +613,37 @@ static WsN carve_n(void* ws, long long Ncap, int num_tiles) {
     return b;
 }
 
-template <int NBITS>
-static void launch_pass(int T, const unsigned int* ki, const unsigned int* vi, unsigned int* ko, unsigned int* vo, int N_cap,
-                        const int* n_dev, int shift, unsigned int* counts, unsigned int* totals, cudaStream_t s) {
+template <int NBITS, int ITEMS, int NEXT>
+static cudaError_t launch_scatter(int T, const unsigned int* ki, const unsigned int* vi, unsigned int* ko, unsigned int* vo,
+                                  int N_cap, const int* n_dev, int shift, unsigned int* counts, unsigned int* totals,
+                                  const RsAux& aux, cudaStream_t s) {
     static bool attr = false;
     if (!attr) {  // shared memory, not L1, is what the scatter kernel lives on
-        cudaFuncSetAttribute(rs_scatter_kernel<NBITS>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        cudaFuncSetAttribute(rs_scatter_kernel<NBITS, ITEMS, NEXT>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         attr = true;
     }
-    rs_tile_hist_kernel<NBITS><<<T, kRsThreads, 0, s>>>(ki, N_cap, n_dev, shift, T, counts);
-    rs_tile_scan_kernel<<<1 << NBITS, 1024, 0, s>>>(counts, T, totals);
-    rs_scatter_kernel<NBITS><<<T, kRsThreads, 0, s>>>(ki, vi, ko, vo, N_cap, n_dev, shift, T, counts, totals);
+    return launch_k(rs_scatter_kernel<NBITS, ITEMS, NEXT>, dim3(T), dim3(kRsThreads), 0, s, ki, vi, ko, vo, N_cap, n_dev, shift, T,
+                    (const unsigned int*)counts, (const unsigned int*)totals, aux);
 }
 
-// one stable LSD radix sort over the low `total_bits` key bits; result lands in (k[passes&1], v[passes&1]).
+// N-level: stable LSD radix sort over the low `total_bits` key bits, three chain-free kernels per pass
+// (histogram, scan over tiles, scatter); result lands in (k[passes&1], v[passes&1]).
 // counts: kRadix * T words of scratch, totals: kRadix words (neither needs initialising)
-static int radix_sort_u32(unsigned int* k[2], unsigned int* v[2], int N_cap, const int* n_dev, int total_bits,
-                          unsigned int* counts, unsigned int* totals, cudaStream_t s) {
+static int radix_sort_n(unsigned int* k[2], unsigned int* v[2], int N_cap, const int* n_dev, int total_bits,
+                        unsigned int* counts, unsigned int* totals, cudaStream_t s) {
     const RsDigits dg = make_digits(total_bits);
-    const int T = (N_cap + kRsTile - 1) / kRsTile;
+    const int T = (N_cap + kRsThreads * kItemsN - 1) / (kRsThreads * kItemsN);
+    const RsAux none = {nullptr, 0, nullptr, nullptr};
     for (int p = 0; p < dg.passes; p++) {
         const unsigned int *ki = k[p & 1], *vi = v[p & 1];
         unsigned int *ko = k[(p + 1) & 1], *vo = v[(p + 1) & 1];
         switch (dg.bits[p]) {
-#define PXB_PASS(B) case B: launch_pass<B>(T, ki, vi, ko, vo, N_cap, n_dev, dg.shift[p], counts, totals, s); break;
+#define PXB_PASS(B)                                                                                                      \
+    case B:                                                                                                              \
+        PXB_CUDA_OK(launch_k(rs_tile_hist_kernel<B, kItemsN>, dim3(T), dim3(kRsThreads), 0, s, ki, N_cap, n_dev, dg.shift[p], T, counts)); \
+        PXB_CUDA_OK(launch_k(rs_tile_scan_kernel, dim3(1 << B), dim3(1024), 0, s, counts, T, totals));                  \
+        PXB_CUDA_OK((launch_scatter<B, kItemsN, kNextNone>(T, ki, vi, ko, vo, N_cap, n_dev, dg.shift[p], counts, totals, none, s))); \
+        break;
             PXB_PASS(1) PXB_PASS(2) PXB_PASS(3) PXB_PASS(4) PXB_PASS(5) PXB_PASS(6) PXB_PASS(7) PXB_PASS(8)
 #undef PXB_PASS
         }
@@ -575,45 +664,72 @@ size_t pxb_bin_sort_workspace_bytes(long long N_cap, int W, int H) {
     return carve_n(nullptr, N_cap > 0 ? N_cap : 1, gx * gy).total;
 }
 
-// Depth-order the Gaussians and prefix-sum their tile counts in that order.
+// Depth-order the visible Gaussians and count the intersections.
 // *total_dev = number of intersections N.  ws_p must stay untouched until pxb_sort_gaussian.
 int pxb_bin_prepare(int P, const float* depth, const int* radius, const int* tiles, int* total_dev, void* ws_p,
                     size_t ws_p_bytes, void* stream) {
-    return pxb::bin_prepare(P, depth, radius, tiles, total_dev, nullptr, ws_p, ws_p_bytes, stream);
+    return pxb::bin_prepare(P, depth, radius, tiles, total_dev, /*counted=*/0, ws_p, ws_p_bytes, stream);
 }
 
 }  // extern "C"
 
-// total_host: optional pinned (device-mapped) host word that also receives the count
-int pxb::bin_prepare(int P, const float* depth, const int* radius, const int* tiles, int* total_dev, int* total_host,
+// the control block of the P-level workspace (counters accumulated by atomics): zero it before the fused
+// forward (which counts the visible Gaussians itself) / at the start of bin_prepare
+int pxb::bin_clear(int P, void* ws_p, size_t ws_p_bytes, void* stream) {
+    WsP b = carve_p(ws_p, P > 0 ? P : 1);
+    if (ws_p_bytes < b.total) return PXB_ERR_WORKSPACE;
+    return (int)cudaMemsetAsync(b.ctl, 0, b.ctl_bytes, (cudaStream_t)stream);
+}
+unsigned int* pxb::bin_vis_counters(int P, void* ws_p) { return carve_p(ws_p, P > 0 ? P : 1).vis_cnt; }
+
+// counted != 0: the control block was cleared by bin_clear and the per-chunk visible counts are already
+// accumulated (fused forward); *total_dev is then left to the key emission (pxb::sort_gaussian publishes it)
+int pxb::bin_prepare(int P, const float* depth, const int* radius, const int* tiles, int* total_dev, int counted,
                      void* ws_p, size_t ws_p_bytes, void* stream) {
     cudaStream_t s = (cudaStream_t)stream;
     if (P <= 0) return (int)cudaMemsetAsync(total_dev, 0, sizeof(int), s);
     WsP b = carve_p(ws_p, P);
     if (ws_p_bytes < b.total) return PXB_ERR_WORKSPACE;
-    PXB_CUDA_OK(cudaMemsetAsync(b.ctl, 0, b.ctl_bytes, s));
-    init_depth_keys_kernel<<<(P + 255) / 256, 256, 0, s>>>(P, depth, b.keys[0], b.vals[0]);
-    int rc = radix_sort_u32(b.keys, b.vals, P, nullptr, 32, b.counts, b.totals, s);  // -> keys[0]/vals[0]
-    if (rc) return rc;
-    scan_kernel<<<(P + kScanTile - 1) / kScanTile, kScanThreads, 0, s>>>(P, tiles, radius, b.vals[0], b.offsets, total_dev,
-                                                                        total_host, b.scan_status, b.scan_ticket);
+    const int nchunk = (P + kCompChunk - 1) / kCompChunk;
+    if (!counted) {
+        PXB_CUDA_OK(cudaMemsetAsync(b.ctl, 0, b.ctl_bytes, s));
+        PXB_CUDA_OK(launch_k(count_visible_kernel, dim3(nchunk), dim3(kCompThreads), 0, s, P, radius, tiles, b.vis_cnt));
+    }
+    constexpr int LOG_P = 11;  // kItemsP * 256 = 2048 pairs per chunk
+    PXB_CUDA_OK(launch_k(compact_kernel, dim3(nchunk), dim3(kCompThreads), 0, s, P, depth, radius, tiles,
+                         (const unsigned int*)b.vis_cnt, b.keys[0], b.vals[0], b.m_dev, b.counts[0], b.T, LOG_P));
+    // 4 passes x 8 bits over the M visible pairs; pass p's scatter accumulates pass p+1's histogram, the last
+    // one the per-chunk tile sums the key emission starts from
+    for (int p = 0; p < 4; p++) {
+        const unsigned int *ki = b.keys[p & 1], *vi = b.vals[p & 1];
+        unsigned int *ko = b.keys[(p + 1) & 1], *vo = b.vals[(p + 1) & 1];
+        PXB_CUDA_OK(launch_k(rs_tile_scan_kernel, dim3(kRadix), dim3(1024), 0, s, b.counts[p], b.T, b.totals));
+        if (p < 3) {
+            const RsAux aux = {b.counts[p + 1], 8 * (p + 1), nullptr, nullptr};
+            PXB_CUDA_OK((launch_scatter<8, kItemsP, kNextHist>(b.T, ki, vi, ko, vo, P, b.m_dev, 8 * p, b.counts[p], b.totals, aux, s)));
+        } else {
+            const RsAux aux = {nullptr, 0, tiles, b.chunk_tiles};
+            PXB_CUDA_OK((launch_scatter<8, kItemsP, kNextTiles>(b.T, ki, vi, ko, vo, P, b.m_dev, 8 * p, b.counts[p], b.totals, aux, s)));
+        }
+    }
+    if (!counted)
+        PXB_CUDA_OK(launch_k(sum_chunks_kernel, dim3(1), dim3(256), 0, s, (const int*)b.m_dev, (const int*)b.chunk_tiles, total_dev));
     return (int)cudaGetLastError();
 }
 
-extern "C" {
-
 // keys + tile sort + ranges.  N: exact count when total_dev == NULL, else a capacity: the kernels
 // then process min(*total_dev, N) intersections and the caller verifies *total_dev <= N afterwards.
-int pxb_sort_gaussian(int P, long long N, const int* total_dev, const float* uv, int uv_stride, int tight,
-                      const float* depth, const int* radius, const int* tiles, int W, int H, int* idx_sorted, int* tile_range,
-                      long long* keys_sorted_out /*nullable, [N]*/, void* ws_p, size_t ws_p_bytes, void* ws_n,
-                      size_t ws_n_bytes, void* stream) {
+// publish != 0: the key emission writes the count to *total_dev (and to the pinned word total_host).
+int pxb::sort_gaussian(int P, long long N, int* total_dev, int publish, int* total_host, const float* uv, int uv_stride,
+                       int tight, const int* rect, const float* depth, const int* radius, const int* tiles, int W, int H,
+                       int* idx_sorted, int* tile_range, long long* keys_sorted_out, void* ws_p, size_t ws_p_bytes,
+                       void* ws_n, size_t ws_n_bytes, void* stream) {
     cudaStream_t s = (cudaStream_t)stream;
     const int gx = (W + PXB_TILE - 1) / PXB_TILE, gy = (H + PXB_TILE - 1) / PXB_TILE;
     const int num_tiles = gx * gy;
     PXB_CUDA_OK(cudaMemsetAsync(tile_range, 0, (size_t)num_tiles * 2 * sizeof(int), s));
     if (P <= 0 || N <= 0) return 0;
-    if (N > 0x3fffffffll || (tight && uv_stride < 6)) return PXB_ERR_BAD_ARG;
+    if (N > 0x3fffffffll || (tight && rect == nullptr && uv_stride < 6) || gx > 0xffff || gy > 0x7fff) return PXB_ERR_BAD_ARG;
     WsP bp = carve_p(ws_p, P);
     WsN bn = carve_n(ws_n, N, num_tiles);
     if (ws_p_bytes < bp.total || ws_n_bytes < bn.total) return PXB_ERR_WORKSPACE;
@@ -623,15 +739,25 @@ int pxb_sort_gaussian(int P, long long N, const int* total_dev, const float* uv,
     unsigned int* v[2];
     v[passes & 1] = (unsigned int*)idx_sorted;
     v[(passes + 1) & 1] = bn.vals_tmp;
-    emit_keys_kernel<<<(P + kEmitThreads - 1) / kEmitThreads, kEmitThreads, 0, s>>>(
-        P, uv, uv_stride, radius, tiles, bp.vals[0], bp.offsets, gx, gy, tight, N, total_dev, k[0], v[0]);
-    int rc = radix_sort_u32(k, v, (int)N, total_dev, tile_bits(num_tiles), bn.counts, bn.totals, s);
+    int* n_sink = publish ? total_dev : (int*)(bp.m_dev + 1);  // scratch word of the control block otherwise
+    PXB_CUDA_OK(launch_k(emit_keys_kernel, dim3((P + kCompChunk - 1) / kCompChunk), dim3(kEmitThreads), 0, s,
+                         (const int*)bp.m_dev, uv, uv_stride, radius, tiles, (const int2*)rect, (const unsigned int*)bp.vals[0],
+                         (const int*)bp.chunk_tiles, gx, gy, tight, N, n_sink, publish ? total_host : (int*)nullptr, k[0], v[0]));
+    int rc = radix_sort_n(k, v, (int)N, total_dev, tile_bits(num_tiles), bn.counts, bn.totals, s);
     if (rc) return rc;
     const unsigned int* tile_sorted = k[passes & 1];
-    tile_range_kernel<<<(int)((N + 1023) / 1024), 256, 0, s>>>((int)N, total_dev, tile_sorted, num_tiles, (int2*)tile_range);
+    PXB_CUDA_OK(launch_k(tile_range_kernel, dim3((int)((N + 1023) / 1024)), dim3(256), 0, s, (int)N, (const int*)total_dev,
+                         tile_sorted, num_tiles, (int2*)tile_range));
     if (keys_sorted_out && total_dev == nullptr)
         rebuild_keys_kernel<<<(int)((N + 255) / 256), 256, 0, s>>>((int)N, tile_sorted, idx_sorted, depth, keys_sorted_out);
     return (int)cudaGetLastError();
 }
 
-}  // extern "C"
+extern "C" int pxb_sort_gaussian(int P, long long N, const int* total_dev, const float* uv, int uv_stride, int tight,
+                                 const float* depth, const int* radius, const int* tiles, int W, int H, int* idx_sorted,
+                                 int* tile_range, long long* keys_sorted_out, void* ws_p, size_t ws_p_bytes, void* ws_n,
+                                 size_t ws_n_bytes, void* stream) {
+    return pxb::sort_gaussian(P, N, const_cast<int*>(total_dev), /*publish=*/0, nullptr, uv, uv_stride, tight, nullptr, depth,
+                              radius, tiles, W, H, idx_sorted, tile_range, keys_sorted_out, ws_p, ws_p_bytes, ws_n, ws_n_bytes,
+                              stream);
+}

@@ -251,9 +251,53 @@ __device__ __forceinline__ unsigned lane_id() { return threadIdx.x & 31u; }
         if (_e != cudaSuccess) return (int)_e; \
     } while (0)
 
-// library-internal (not part of the C ABI): pxb_bin_prepare with an optional pinned, device-mapped host
-// word that also receives the intersection count (binning.cu)
-int bin_prepare(int P, const float* depth, const int* radius, const int* tiles, int* total_dev, int* total_host,
-                void* ws_p, size_t ws_p_bytes, void* stream);
+// ---- programmatic dependent launch (PDL) ---------------------------------------------------------
+// The render path is a chain of ~25 short kernels per view.  Every kernel of the chain starts with
+// pdl_wait() (griddepcontrol.wait: returns once the preceding kernel of the stream has completed and its
+// writes are visible) and is launched through launch_k() with programmatic stream serialization, so its
+// launch latency and CTA scheduling overlap the tail of its predecessor instead of following it.  A
+// kernel launched this way MUST call pdl_wait() before its first global-memory access.  No kernel
+// triggers early (griddepcontrol.launch_dependents is not used): correctness never depends on PDL, and
+// PXB_PDL=0 in the environment launches everything with plain stream ordering (A/B measurements).
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+bool pdl_enabled();  // pipeline.cu
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
+// library-internal (not part of the C ABI), binning.cu: the stages of pxb_bin_prepare / pxb_sort_gaussian
+// as the whole-view entry point (pipeline.cu) drives them.
+//   bin_clear        zero the control block of the P-level workspace (before the fused forward counts into it)
+//   bin_vis_counters the per-1024-Gaussian visible counters inside that block
+//   bin_prepare      counted != 0: those counters are already filled; *total_dev is left to the key emission
+//   sort_gaussian    publish != 0: the key emission stores the intersection count into *total_dev and into the
+//                    pinned, device-mapped host word total_host (nullable); rect: the fused forward's tile
+//                    rectangles {x0 | y0 << 16, w | h << 16} (nullable: recomputed from uv / radius)
+int fused_forward(int P, int sh_degree, const float* pos, const float* scales, const float* quats, const float* opacity,
+                  const float* shs, const float* extra, int n_extra, int with_depth, const float* intr, const float* extr,
+                  const float* cam_center, int W, int H, float nearest, float extent, int S, int tight, float* rec,
+                  float* depth, int* radius, int* tiles, int* rect /*int2[P], nullable*/, unsigned int* vis_cnt /*nullable*/,
+                  void* stream);
+int bin_clear(int P, void* ws_p, size_t ws_p_bytes, void* stream);
+unsigned int* bin_vis_counters(int P, void* ws_p);
+int bin_prepare(int P, const float* depth, const int* radius, const int* tiles, int* total_dev, int counted, void* ws_p,
+                size_t ws_p_bytes, void* stream);
+int sort_gaussian(int P, long long N, int* total_dev, int publish, int* total_host, const float* uv, int uv_stride,
+                  int tight, const int* rect, const float* depth, const int* radius, const int* tiles, int W, int H,
+                  int* idx_sorted, int* tile_range, long long* keys_sorted_out, void* ws_p, size_t ws_p_bytes, void* ws_n,
+                  size_t ws_n_bytes, void* stream);
 
 }  // namespace pxb

@@ -5,15 +5,26 @@
 //
 // The intersection count reaches the host without a memcpy in the stream: the scan kernel stores it
 // into a pinned, device-mapped host word the caller polls while the blend kernel is already queued.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "pointrix_b200.h"
 
 using namespace pxb;
 
+// PXB_PDL=0 switches programmatic dependent launch off (common.cuh)
+bool pxb::pdl_enabled() {
+    static const bool on = [] {
+        const char* e = getenv("PXB_PDL");
+        return !(e && e[0] == '0');
+    }();
+    return on;
+}
+
 namespace {
 
 struct WsRender {
-    int* tiles; int* total_dev; void* ws_p; size_t ws_p_bytes; void* ws_n; size_t ws_n_bytes;
+    int* tiles; int* rect; int* total_dev; void* ws_p; size_t ws_p_bytes; void* ws_n; size_t ws_n_bytes;
     size_t total;
 };
 
@@ -25,6 +36,7 @@ WsRender carve(void* ws, int P, long long N_cap, int W, int H) {
     size_t o = 0;
     b.total_dev = (int*)(base + o); o += 256;
     b.tiles = (int*)(base + o); o += up256((size_t)(P > 0 ? P : 1) * 4);
+    b.rect = (int*)(base + o); o += up256((size_t)(P > 0 ? P : 1) * 8);  // int2 per Gaussian
     b.ws_p_bytes = pxb_bin_prepare_workspace_bytes(P);
     b.ws_p = base + o; o += up256(b.ws_p_bytes);
     b.ws_n_bytes = pxb_bin_sort_workspace_bytes(N_cap, W, H);
@@ -57,16 +69,20 @@ int pxb_render_forward(int P, int sh_degree, const float* pos, const float* scal
     const WsRender b = carve(ws, P, N_cap, W, H);
     if (ws_bytes < b.total) return PXB_ERR_WORKSPACE;
     int rc;
+    // the binning counters the fused forward accumulates into (visible Gaussians per 1024 ids) are zeroed first
+    if ((rc = bin_clear(P, b.ws_p, b.ws_p_bytes, stream))) return rc;
     if ((rc = mark(stage_events, 0, s))) return rc;
-    rc = pxb_fused_forward(P, sh_degree, pos, scales, quats, opacity, shs, extra, n_extra, with_depth, intr, extr,
-                           cam_center, W, H, nearest, extent, S, /*tight=*/1, rec, depth, radius, b.tiles, stream);
+    rc = fused_forward(P, sh_degree, pos, scales, quats, opacity, shs, extra, n_extra, with_depth, intr, extr, cam_center,
+                       W, H, nearest, extent, S, /*tight=*/1, rec, depth, radius, b.tiles, b.rect,
+                       bin_vis_counters(P, b.ws_p), stream);
     if (rc) return rc;
     if ((rc = mark(stage_events, 1, s))) return rc;
-    rc = bin_prepare(P, depth, radius, b.tiles, b.total_dev, total_host, b.ws_p, b.ws_p_bytes, stream);
+    rc = bin_prepare(P, depth, radius, b.tiles, b.total_dev, /*counted=*/1, b.ws_p, b.ws_p_bytes, stream);
     if (rc) return rc;
     if ((rc = mark(stage_events, 2, s))) return rc;
-    rc = pxb_sort_gaussian(P, N_cap, b.total_dev, rec, S, /*tight=*/1, depth, radius, b.tiles, W, H, idx_sorted,
-                           tile_range, nullptr, b.ws_p, b.ws_p_bytes, b.ws_n, b.ws_n_bytes, stream);
+    // the key emission publishes the intersection count (device word + the pinned host word the caller polls)
+    rc = sort_gaussian(P, N_cap, b.total_dev, /*publish=*/1, total_host, rec, S, /*tight=*/1, b.rect, depth, radius,
+                       b.tiles, W, H, idx_sorted, tile_range, nullptr, b.ws_p, b.ws_p_bytes, b.ws_n, b.ws_n_bytes, stream);
     if (rc) return rc;
     if ((rc = mark(stage_events, 3, s))) return rc;
     rc = pxb_blend_forward(rec, S, C, idx_sorted, tile_range, bg, W, H, final_T, ncontrib, out, stream);

@@ -428,7 +428,9 @@ fused_fwd_kernel(int P, const float* __restrict__ pos, const float* __restrict__
                  int with_depth, const float* __restrict__ intr, const float* __restrict__ extr,
                  const float* __restrict__ cam_center, int W, int H, int gx, int gy, float nearest,
                  float extent, int S, int tight, float* __restrict__ rec, float* __restrict__ depth,
-                 int* __restrict__ radius, int* __restrict__ tiles) {
+                 int* __restrict__ radius, int* __restrict__ tiles, int2* __restrict__ rect /*nullable*/,
+                 unsigned int* __restrict__ vis_cnt /*nullable: visible Gaussians per 1024 ids, accumulated*/) {
+    pdl_wait();
     extern __shared__ __align__(16) float sh_smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -461,9 +463,25 @@ fused_fwd_kernel(int P, const float* __restrict__ pos, const float* __restrict__
             }
         }
     }
+    // the tile rectangle binning will expand -- computed ONCE, here: the key emission reads it back instead of
+    // re-deriving it (tight: only the tiles the alpha >= 1/255 ellipse can reach, common.cuh)
+    const float op_i = i < P ? opacity[i] : 0.f;
+    int2 rc = make_int2(0, 0);
+    if (rad > 0) {
+        int x0, y0, x1, y1;
+        if (tight) tight_tile_rect(u, v, rad, cn[0], cn[1], cn[2], op_i, gx, gy, x0, y0, x1, y1);
+        else tile_rect(u, v, rad, gx, gy, x0, y0, x1, y1);
+        nt = (x1 - x0) * (y1 - y0);
+        if (nt > 0) rc = make_int2(x0 | (y0 << 16), (x1 - x0) | ((y1 - y0) << 16));
+    }
+    if (vis_cnt != nullptr) {  // a warp's 32 ids share one 1024-id chunk
+        const unsigned int vm = __ballot_sync(0xffffffffu, rad > 0 && nt > 0);
+        if (lane == 0 && vm) atomicAdd(&vis_cnt[(blockIdx.x * blockDim.x + warp * 32) >> 10], (unsigned int)__popc(vm));
+    }
     cp_async_wait_all();
     __syncwarp();
     if (i >= P) return;
+    if (rect != nullptr) rect[i] = rc;
     // SH colour: rgb = max(sum + 0.5, 0)   (msplat.py:94-105)
     float rgb[3];
     {
@@ -492,12 +510,6 @@ fused_fwd_kernel(int P, const float* __restrict__ pos, const float* __restrict__
     // culled Gaussians: uv = 0, depth = 0, as project_point leaves them
     const float dep = keep ? t.z : 0.f;
     if (!keep) { u = 0.f; v = 0.f; }
-    const float op_i = opacity[i];
-    if (tight && rad > 0) {  // count only the tiles the alpha >= 1/255 ellipse can reach (common.cuh)
-        int x0, y0, x1, y1;
-        tight_tile_rect(u, v, rad, cn[0], cn[1], cn[2], op_i, gx, gy, x0, y0, x1, y1);
-        nt = (x1 - x0) * (y1 - y0);
-    }
     depth[i] = dep;
     radius[i] = rad;
     tiles[i] = nt;
@@ -880,6 +892,17 @@ int pxb_fused_forward(int P, int sh_degree, const float* pos, const float* scale
                       const float* opacity, const float* shs, const float* extra, int n_extra, int with_depth,
                       const float* intr, const float* extr, const float* cam_center, int W, int H, float nearest,
                       float extent, int S, int tight, float* rec, float* depth, int* radius, int* tiles, void* stream) {
+    return pxb::fused_forward(P, sh_degree, pos, scales, quats, opacity, shs, extra, n_extra, with_depth, intr, extr,
+                              cam_center, W, H, nearest, extent, S, tight, rec, depth, radius, tiles, nullptr, nullptr, stream);
+}
+
+}  // extern "C"
+
+int pxb::fused_forward(int P, int sh_degree, const float* pos, const float* scales, const float* quats,
+                       const float* opacity, const float* shs, const float* extra, int n_extra, int with_depth,
+                       const float* intr, const float* extr, const float* cam_center, int W, int H, float nearest,
+                       float extent, int S, int tight, float* rec, float* depth, int* radius, int* tiles, int* rect,
+                       unsigned int* vis_cnt, void* stream) {
     if (P <= 0) return 0;
     if (sh_degree < 0 || sh_degree > 3) return PXB_ERR_UNSUPPORTED;
     if (S % 4 != 0 || S < 6 + 3 + with_depth + n_extra) return PXB_ERR_BAD_ARG;
@@ -888,10 +911,11 @@ int pxb_fused_forward(int P, int sh_degree, const float* pos, const float* scale
     cudaStream_t s = (cudaStream_t)stream;
     const int nb = blocks_for(P, kFThreads);
     const size_t smem = (size_t)kFThreads * kShPitch * sizeof(float);
-#define PXB_LAUNCH_FWD(KA)                                                                                         \
-    fused_fwd_kernel<KA><<<nb, kFThreads, smem, s>>>(P, pos, scales, (const float4*)quats, opacity, shs, extra,    \
-                                                     n_extra, with_depth, intr, extr, cam_center, W, H, gx, gy,    \
-                                                     nearest, extent, S, tight, rec, depth, radius, tiles)
+    if (gx > 0xffff || gy > 0x7fff) return PXB_ERR_BAD_ARG;  // the packed rectangle holds 16-bit tile coordinates
+#define PXB_LAUNCH_FWD(KA)                                                                                              \
+    PXB_CUDA_OK(launch_k(fused_fwd_kernel<KA>, dim3(nb), dim3(kFThreads), smem, s, P, pos, scales, (const float4*)quats,   \
+                         opacity, shs, extra, n_extra, with_depth, intr, extr, cam_center, W, H, gx, gy, nearest, extent, \
+                         S, tight, rec, depth, radius, tiles, (int2*)rect, vis_cnt))
     switch (sh_degree) {
         case 0: PXB_LAUNCH_FWD(1); break;
         case 1: PXB_LAUNCH_FWD(4); break;
@@ -901,6 +925,8 @@ int pxb_fused_forward(int P, int sh_degree, const float* pos, const float* scale
 #undef PXB_LAUNCH_FWD
     return (int)cudaGetLastError();
 }
+
+extern "C" {
 
 int pxb_fused_backward(int P, int sh_degree, const float* pos, const float* scales, const float* quats,
                        const float* shs, int n_extra, int with_depth, const float* intr, const float* extr,

@@ -407,7 +407,7 @@ def test_vs_committed_golden(pb, tag, deg, rd, use_extra):
     r = _renderer(pb, rd, deg)
     leaves = {k: g[k].clone().requires_grad_() for k in ("position", "opacity", "scaling", "rotation", "shs")}
     E, intr, cc = g["E"].clone().requires_grad_(), g["intr"].clone().requires_grad_(), g["cc"].clone().requires_grad_()
-    kw = {"extra": g["extra"]} if use_extra else {}
+    kw = {"extra_features": {"extra": g["extra"]}} if use_extra else {}
     out = r.render_iter(H, W, E, intr, cc, **leaves, **kw)
     img = torch.cat(list(out["rendered_features_split"].values()), 0)
     assert torch.equal(out["radii"], g[f"{tag}_radius"])
