@@ -19,6 +19,8 @@
 // value-halving butterfly (about one shuffle per value instead of five) and
 // land as ONE contiguous vector atomic per (warp, Gaussian) on the gradient
 // record.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "pointrix_b200.h"
 
@@ -143,19 +145,52 @@ __device__ __forceinline__ void write_sentinel(float* sm_rec, int S) {
     if ((int)threadIdx.x < S) sm_rec[kBatch * S + threadIdx.x] = (threadIdx.x == 2 || threadIdx.x == 4) ? 1.f : 0.f;
 }
 
-template <int CH, int S>
+// ---- bulk-copy staging (BULK = true) ----------------------------------------------------------------
+// Every record of a batch is fetched by ONE cp.async.bulk (48 contiguous, 16-byte aligned bytes at C = 3)
+// issued by the thread that owns the slot; the copies of batch b+1 are in flight while batch b is blended
+// (two staging buffers, one mbarrier each, completion by transaction bytes).  The synchronous variant
+// (BULK = false) stages with LDG.128 + STS.128 by all 256 threads and waits for them at a barrier.
+__device__ __forceinline__ void mbar_init(unsigned int bar, unsigned int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned int bar, unsigned int bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned int bar, unsigned int parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(unsigned int dst, const void* src, unsigned int bytes, unsigned int bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+template <int CH, int S, bool BULK>
 __global__ void __launch_bounds__(kBlendThreads)
 blend_fwd_kernel(const float* __restrict__ rec, const int* __restrict__ idx_sorted, const int2* __restrict__ tile_range,
-                 float bg, int C, int W, int H, int gx, float* __restrict__ final_T, int* __restrict__ ncontrib,
-                 float* __restrict__ out) {
+                 const int* __restrict__ tile_order, float bg, int C, int W, int H, int gx, float* __restrict__ final_T,
+                 int* __restrict__ ncontrib, float* __restrict__ out) {
+    pdl_wait();
+    constexpr int NBUF = BULK ? 2 : 1;
     extern __shared__ __align__(16) float sm_f[];
-    float* sm_rec = sm_f;                                                                  // [kBatch + 1][S]
-    unsigned short* sm_list = reinterpret_cast<unsigned short*>(sm_f + (kBatch + 1) * S);  // [8 warps][kBatch + kUnroll]
+    float* sm_rec0 = sm_f;                                                                        // [NBUF][kBatch + 1][S]
+    unsigned short* sm_list = reinterpret_cast<unsigned short*>(sm_f + NBUF * (kBatch + 1) * S);  // [8 warps][kBatch + kUnroll]
     unsigned char* sm_mask = reinterpret_cast<unsigned char*>(sm_list + (kBlendThreads / 32) * (kBatch + kUnroll));
-    const int tile = blockIdx.y * gx + blockIdx.x;
+    __shared__ __align__(8) unsigned long long s_bar[2];
+    // heaviest tiles first (tile_order: tile ids by descending list length): the tail of the grid is made of
+    // short tiles instead of whatever the raster order ends with
+    const int tile = tile_order ? tile_order[blockIdx.x] : (int)blockIdx.x;
+    const int tx = tile % gx, ty = tile / gx;
     int lx, ly;
     thread_pixel(lx, ly);
-    const int pxi = blockIdx.x * PXB_TILE + lx, pyi = blockIdx.y * PXB_TILE + ly;
+    const int pxi = tx * PXB_TILE + lx, pyi = ty * PXB_TILE + ly;
     const bool inside = pxi < W && pyi < H;
     const float pxf = (float)pxi, pyf = (float)pyi;
     // a finished pixel (saturated, or outside the image) raises its alpha threshold above 0.99, the
@@ -169,18 +204,50 @@ blend_fwd_kernel(const float* __restrict__ rec, const int* __restrict__ idx_sort
 #pragma unroll
     for (int k = 0; k < CH; k++) F[k] = 0.f;
     const unsigned warp = threadIdx.x >> 5;
-    const float X0 = (float)(blockIdx.x * PXB_TILE), Y0 = (float)(blockIdx.y * PXB_TILE);
+    const float X0 = (float)(tx * PXB_TILE), Y0 = (float)(ty * PXB_TILE);
     unsigned short* my_list = sm_list + warp * (kBatch + kUnroll);
-    const unsigned int rec_s = opaque_u32((unsigned int)__cvta_generic_to_shared(sm_rec));
+    const unsigned int rec_s0 = opaque_u32((unsigned int)__cvta_generic_to_shared(sm_rec0));
     const unsigned int list_s = opaque_u32((unsigned int)__cvta_generic_to_shared(my_list));
-    write_sentinel(sm_rec, S);
+    write_sentinel(sm_rec0, S);
+    if (BULK) write_sentinel(sm_rec0 + (kBatch + 1) * S, S);
     int n_cand = 0;
-
-    for (int base = 0; todo > 0; base += kBatch, todo -= kBatch) {
-        if (__syncthreads_count(thr > 1.f) == kBlendThreads) break;
-        const int n = min(kBatch, todo);
-        stage_records<S>(sm_rec, nullptr, rec, idx_sorted + range.x + base, n);
+    const unsigned int bar_s = (unsigned int)__cvta_generic_to_shared(&s_bar[0]);
+    // BULK: thread t owns slot t of every batch; issue = one bulk copy of its record into buffer (batch & 1)
+    auto issue = [&](int batch_base, int left, int buf) {
+        const int n = min(kBatch, left);
+        if (threadIdx.x == 0) mbar_expect_tx(bar_s + 8u * buf, (unsigned int)n * (S * 4u));
+        if ((int)threadIdx.x < n) {
+            const int g = idx_sorted[range.x + batch_base + threadIdx.x];
+            bulk_g2s(rec_s0 + (unsigned int)(buf * (kBatch + 1) + threadIdx.x) * (S * 4u), rec + (size_t)g * S, S * 4u,
+                     bar_s + 8u * buf);
+        }
+    };
+    if (BULK) {
+        if (threadIdx.x == 0) {
+            mbar_init(bar_s, 1);
+            mbar_init(bar_s + 8u, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
         __syncthreads();
+        if (todo > 0) issue(0, todo, 0);
+    }
+
+    for (int base = 0, it = 0; todo > 0; base += kBatch, todo -= kBatch, it++) {
+        const int buf = BULK ? (it & 1) : 0;
+        float* sm_rec = sm_rec0 + buf * (kBatch + 1) * S;
+        const unsigned int rec_s = rec_s0 + (unsigned int)(buf * (kBatch + 1)) * (S * 4u);
+        // (the barrier also orders the previous batch's reads of the other buffer before its refill below)
+        const bool all_done = __syncthreads_count(thr > 1.f) == kBlendThreads;
+        const int n = min(kBatch, todo);
+        if (BULK) {
+            if (!all_done && todo > kBatch) issue(base + kBatch, todo - kBatch, buf ^ 1);
+            mbar_wait(bar_s + 8u * buf, (unsigned int)((it >> 1) & 1));  // drain this buffer even when leaving
+            if (all_done) break;
+        } else {
+            if (all_done) break;
+            stage_records<S>(sm_rec, nullptr, rec, idx_sorted + range.x + base, n);
+            __syncthreads();
+        }
         if ((int)threadIdx.x < n) {
             const float4 r0 = *reinterpret_cast<const float4*>(sm_rec + threadIdx.x * S);
             const float2 r1 = *reinterpret_cast<const float2*>(sm_rec + threadIdx.x * S + 4);
@@ -263,8 +330,10 @@ constexpr int kSlotPitch = 33;  // float2 units: conflict-free row (phase 1) and
 template <int CH, int S>
 __global__ void __launch_bounds__(kBlendThreads, (CH <= 4 ? 4 : 1))
 blend_bwd_kernel(const float* __restrict__ rec, const int* __restrict__ idx_sorted, const int2* __restrict__ tile_range,
-                 float bg, int C, int W, int H, int gx, const float* __restrict__ final_T,
-                 const int* __restrict__ ncontrib, const float* __restrict__ dL_dout, float* __restrict__ grec) {
+                 const int* __restrict__ tile_order, float bg, int C, int W, int H, int gx,
+                 const float* __restrict__ final_T, const int* __restrict__ ncontrib, const float* __restrict__ dL_dout,
+                 float* __restrict__ grec) {
+    pdl_wait();
     constexpr int CHP = (CH + 3) & ~3;  // dL/dpix row padded to float4s
     constexpr int NW = kBlendThreads / 32;
     extern __shared__ __align__(16) float sm_f[];
@@ -274,10 +343,11 @@ blend_bwd_kernel(const float* __restrict__ rec, const int* __restrict__ idx_sort
     int* sm_id = reinterpret_cast<int*>(sm_slot + NW * kSlots * kSlotPitch);  // [kBatch]
     unsigned short* sm_list = reinterpret_cast<unsigned short*>(sm_id + kBatch);  // [NW][kBatch]
     unsigned char* sm_mask = reinterpret_cast<unsigned char*>(sm_list + NW * kBatch);  // [kBatch]
-    const int tile = blockIdx.y * gx + blockIdx.x;
+    const int tile = tile_order ? tile_order[blockIdx.x] : (int)blockIdx.x;  // heaviest tiles first, as the forward
+    const int tx = tile % gx, ty = tile / gx;
     int lx, ly;
     thread_pixel(lx, ly);
-    const int pxi = blockIdx.x * PXB_TILE + lx, pyi = blockIdx.y * PXB_TILE + ly;
+    const int pxi = tx * PXB_TILE + lx, pyi = ty * PXB_TILE + ly;
     const float pxf = (float)pxi, pyf = (float)pyi;
     const bool inside = pxi < W && pyi < H;
     const size_t pix = (size_t)pyi * W + pxi;
@@ -306,7 +376,7 @@ blend_bwd_kernel(const float* __restrict__ rec, const int* __restrict__ idx_sort
     if (lane == 0) atomicMax(&s_cta_last, warp_last);
     __syncthreads();
     const int cta_last = s_cta_last;
-    const float X0 = (float)(blockIdx.x * PXB_TILE), Y0 = (float)(blockIdx.y * PXB_TILE);
+    const float X0 = (float)(tx * PXB_TILE), Y0 = (float)(ty * PXB_TILE);
 
     // phase-2 role of this lane: Gaussian slot (lane & 15), pixel half (lane >> 4) = rows 2h, 2h+1 of the block
     float2* slots = sm_slot + warp * (kSlots * kSlotPitch);
@@ -487,27 +557,46 @@ __global__ void unpack_grads_kernel(int P, const float* __restrict__ grec, int S
     for (int k = 0; k < cn; k++) dL_dfeature[(size_t)i * C + c0 + k] = g[6 + k];
 }
 
-template <int CH, int S>
-static int launch_fwd(const float* rec, const int* idx_sorted, const int* tile_range, float bg, int C, int W, int H,
-                      float* final_T, int* ncontrib, float* out, cudaStream_t s) {
+// PXB_BLEND_STAGING=bulk selects the cp.async.bulk + mbarrier double-buffered staging of the forward kernel
+// (measured against the synchronous LDG/STS staging in profiles/)
+static bool bulk_staging() {
+    static const bool on = [] {
+        const char* e = getenv("PXB_BLEND_STAGING");
+        return e && e[0] == 'b';
+    }();
+    return on;
+}
+
+template <int CH, int S, bool BULK>
+static int launch_fwd_v(const float* rec, const int* idx_sorted, const int* tile_range, const int* tile_order, float bg,
+                        int C, int W, int H, float* final_T, int* ncontrib, float* out, cudaStream_t s) {
     const int gx = (W + PXB_TILE - 1) / PXB_TILE, gy = (H + PXB_TILE - 1) / PXB_TILE;
-    const size_t smem = (size_t)(kBatch + 1) * S * 4 + (kBlendThreads / 32) * (kBatch + kUnroll) * 2 + kBatch;
+    const size_t smem = (size_t)(BULK ? 2 : 1) * (kBatch + 1) * S * 4 + (kBlendThreads / 32) * (kBatch + kUnroll) * 2 + kBatch;
     static bool attr = false;
     if (!attr) {
         if (smem > 48 * 1024)
-            PXB_CUDA_OK(cudaFuncSetAttribute(blend_fwd_kernel<CH, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        PXB_CUDA_OK(cudaFuncSetAttribute(blend_fwd_kernel<CH, S>, cudaFuncAttributePreferredSharedMemoryCarveout,
+            PXB_CUDA_OK(cudaFuncSetAttribute(blend_fwd_kernel<CH, S, BULK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        PXB_CUDA_OK(cudaFuncSetAttribute(blend_fwd_kernel<CH, S, BULK>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                          cudaSharedmemCarveoutMaxShared));
         attr = true;
     }
-    blend_fwd_kernel<CH, S><<<dim3(gx, gy), kBlendThreads, smem, s>>>(rec, idx_sorted, (const int2*)tile_range, bg, C, W,
-                                                                      H, gx, final_T, ncontrib, out);
+    PXB_CUDA_OK(launch_k(blend_fwd_kernel<CH, S, BULK>, dim3(gx * gy), dim3(kBlendThreads), smem, s, rec, idx_sorted,
+                         (const int2*)tile_range, tile_order, bg, C, W, H, gx, final_T, ncontrib, out));
     return (int)cudaGetLastError();
 }
 
 template <int CH, int S>
-static int launch_bwd(const float* rec, const int* idx_sorted, const int* tile_range, float bg, int C, int W, int H,
-                      const float* final_T, const int* ncontrib, const float* dL_dout, float* grec, cudaStream_t s) {
+static int launch_fwd(const float* rec, const int* idx_sorted, const int* tile_range, const int* tile_order, float bg, int C,
+                      int W, int H, float* final_T, int* ncontrib, float* out, cudaStream_t s) {
+    if (bulk_staging() && S <= 16)  // two staging buffers: the wide strides keep the single-buffer variant
+        return launch_fwd_v<CH, S, true>(rec, idx_sorted, tile_range, tile_order, bg, C, W, H, final_T, ncontrib, out, s);
+    return launch_fwd_v<CH, S, false>(rec, idx_sorted, tile_range, tile_order, bg, C, W, H, final_T, ncontrib, out, s);
+}
+
+template <int CH, int S>
+static int launch_bwd(const float* rec, const int* idx_sorted, const int* tile_range, const int* tile_order, float bg, int C,
+                      int W, int H, const float* final_T, const int* ncontrib, const float* dL_dout, float* grec,
+                      cudaStream_t s) {
     const int gx = (W + PXB_TILE - 1) / PXB_TILE, gy = (H + PXB_TILE - 1) / PXB_TILE;
     constexpr int CHP = (CH + 3) & ~3, NW = kBlendThreads / 32;
     const size_t smem = (size_t)(kBatch * S + NW * 32 * CHP + 2 * NW * kSlots * kSlotPitch) * 4 + kBatch * 4 + NW * kBatch * 2 + kBatch;
@@ -519,8 +608,8 @@ static int launch_bwd(const float* rec, const int* idx_sorted, const int* tile_r
                                          cudaSharedmemCarveoutMaxShared));
         attr = true;
     }
-    blend_bwd_kernel<CH, S><<<dim3(gx, gy), kBlendThreads, smem, s>>>(
-        rec, idx_sorted, (const int2*)tile_range, bg, C, W, H, gx, final_T, ncontrib, dL_dout, grec);
+    PXB_CUDA_OK(launch_k(blend_bwd_kernel<CH, S>, dim3(gx * gy), dim3(kBlendThreads), smem, s, rec, idx_sorted,
+                         (const int2*)tile_range, tile_order, bg, C, W, H, gx, final_T, ncontrib, dL_dout, grec));
     return (int)cudaGetLastError();
 }
 
@@ -559,23 +648,24 @@ int pxb_record_stride(int C) {
     return -1;
 }
 
-int pxb_blend_forward(const float* rec, int S, int C, const int* idx_sorted, const int* tile_range, float bg, int W,
-                      int H, float* final_T, int* ncontrib, float* out, void* stream) {
+int pxb_blend_forward(const float* rec, int S, int C, const int* idx_sorted, const int* tile_range,
+                      const int* tile_order, float bg, int W, int H, float* final_T, int* ncontrib, float* out,
+                      void* stream) {
     cudaStream_t s = (cudaStream_t)stream;
     if (W <= 0 || H <= 0) return 0;
     if (C < 1 || C > PXB_MAX_CHANNELS_PER_PASS || S != pxb_record_stride(C)) return PXB_ERR_BAD_ARG;
     if (((uintptr_t)rec) & 15) return PXB_ERR_ALIGN;
-    PXB_BLEND_DISPATCH(launch_fwd, rec, idx_sorted, tile_range, bg, C, W, H, final_T, ncontrib, out, s)
+    PXB_BLEND_DISPATCH(launch_fwd, rec, idx_sorted, tile_range, tile_order, bg, C, W, H, final_T, ncontrib, out, s)
 }
 
-int pxb_blend_backward(const float* rec, int S, int C, const int* idx_sorted, const int* tile_range, float bg, int W,
-                       int H, const float* final_T, const int* ncontrib, const float* dL_dout, float* grec,
-                       void* stream) {
+int pxb_blend_backward(const float* rec, int S, int C, const int* idx_sorted, const int* tile_range,
+                       const int* tile_order, float bg, int W, int H, const float* final_T, const int* ncontrib,
+                       const float* dL_dout, float* grec, void* stream) {
     cudaStream_t s = (cudaStream_t)stream;
     if (W <= 0 || H <= 0) return 0;
     if (C < 1 || C > PXB_MAX_CHANNELS_PER_PASS || S != pxb_record_stride(C)) return PXB_ERR_BAD_ARG;
     if ((((uintptr_t)rec) | ((uintptr_t)grec)) & 15) return PXB_ERR_ALIGN;
-    PXB_BLEND_DISPATCH(launch_bwd, rec, idx_sorted, tile_range, bg, C, W, H, final_T, ncontrib, dL_dout, grec, s)
+    PXB_BLEND_DISPATCH(launch_bwd, rec, idx_sorted, tile_range, tile_order, bg, C, W, H, final_T, ncontrib, dL_dout, grec, s)
 }
 
 // counters: device pointer to >= 2 unsigned 64-bit words (NULL switches counting off).  Slot 0 accumulates

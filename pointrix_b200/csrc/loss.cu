@@ -97,6 +97,7 @@ template <bool STORE>
 __global__ void __launch_bounds__(kLThreads)
 l1_ssim_fwd_kernel(int H, int W, const float* __restrict__ pred, const float* __restrict__ gt,
                    float* __restrict__ dmaps, size_t map_stride, float* __restrict__ partial, GaussWin gw) {
+    pdl_wait();
     __shared__ __align__(16) float sx[kLI][kLP];
     __shared__ __align__(16) float sy[kLI][kLP];
     __shared__ __align__(16) float hs[5][kLI][kLT];
@@ -201,6 +202,7 @@ l1_ssim_fwd_kernel(int H, int W, const float* __restrict__ pred, const float* __
 __global__ void __launch_bounds__(256)
 loss_finalize_kernel(const float* __restrict__ partial, size_t nblk, size_t per_image, double inv_count, float* out0,
                      float* out1) {
+    pdl_wait();
     __shared__ double red[2][256];
     const int b = blockIdx.x;
     double s0 = 0.0, s1 = 0.0;
@@ -225,6 +227,7 @@ loss_finalize_kernel(const float* __restrict__ partial, size_t nblk, size_t per_
 __global__ void __launch_bounds__(256)
 loss_finalize_fused_kernel(const float* __restrict__ partial, size_t nblk, double inv_count, float lambda,
                            float* __restrict__ out3) {
+    pdl_wait();
     __shared__ double red[2][256];
     double s0 = 0.0, s1 = 0.0;
     for (size_t i = threadIdx.x; i < nblk; i += 256) s0 += (double)partial[i], s1 += (double)partial[nblk + i];
@@ -247,6 +250,7 @@ l1_ssim_bwd_kernel(int C, int H, int W, const float* __restrict__ pred, const fl
                    const float* __restrict__ dmaps, size_t map_stride, const float* __restrict__ g_l1,
                    const float* __restrict__ g_ssim, int g_stride, float s_l1, float s_ssim,
                    float* __restrict__ d_pred, GaussWin gw) {
+    pdl_wait();
     __shared__ __align__(16) float sm[3][kLI][kLP];
     __shared__ __align__(16) float hs[3][kLI][kLT];
 
@@ -376,9 +380,9 @@ static int l1_ssim_launch(int B, int C, int H, int W, const float* pred, const f
     const size_t map_stride = (size_t)B * C * H * W;
     float* partial = (float*)ws;
     if (dmaps)
-        l1_ssim_fwd_kernel<true><<<grid, kLThreads, 0, st>>>(H, W, pred, gt, dmaps, map_stride, partial, gw);
+        PXB_CUDA_OK(launch_k(l1_ssim_fwd_kernel<true>, grid, dim3(kLThreads), 0, st, H, W, pred, gt, dmaps, map_stride, partial, gw));
     else
-        l1_ssim_fwd_kernel<false><<<grid, kLThreads, 0, st>>>(H, W, pred, gt, nullptr, map_stride, partial, gw);
+        PXB_CUDA_OK(launch_k(l1_ssim_fwd_kernel<false>, grid, dim3(kLThreads), 0, st, H, W, pred, gt, (float*)nullptr, map_stride, partial, gw));
     *nblk_out = (size_t)grid.x * grid.y * grid.z;
     return 0;
 }
@@ -390,8 +394,8 @@ int pxb_l1_ssim_forward(int B, int C, int H, int W, const float* pred, const flo
     size_t nblk = 0;
     const int rc = l1_ssim_launch(B, C, H, W, pred, gt, dmaps, ws, ws_bytes, st, &nblk);
     if (rc) return rc;
-    loss_finalize_kernel<<<B, 256, 0, st>>>((const float*)ws, nblk, nblk / B, 1.0 / ((double)C * H * W), l1_mean,
-                                            ssim_mean);
+    PXB_CUDA_OK(launch_k(loss_finalize_kernel, dim3(B), dim3(256), 0, st, (const float*)ws, nblk, nblk / B,
+                         1.0 / ((double)C * H * W), l1_mean, ssim_mean));
     return (int)cudaGetLastError();
 }
 
@@ -402,8 +406,8 @@ int pxb_l1_ssim_loss_forward(int B, int C, int H, int W, const float* pred, cons
     size_t nblk = 0;
     const int rc = l1_ssim_launch(B, C, H, W, pred, gt, dmaps, ws, ws_bytes, st, &nblk);
     if (rc) return rc;
-    loss_finalize_fused_kernel<<<1, 256, 0, st>>>((const float*)ws, nblk, 1.0 / ((double)B * C * H * W), lambda_ssim,
-                                                  loss3);
+    PXB_CUDA_OK(launch_k(loss_finalize_fused_kernel, dim3(1), dim3(256), 0, st, (const float*)ws, nblk,
+                         1.0 / ((double)B * C * H * W), lambda_ssim, loss3));
     return (int)cudaGetLastError();
 }
 
@@ -414,8 +418,8 @@ int pxb_l1_ssim_backward(int B, int C, int H, int W, const float* pred, const fl
     if ((long long)B * C > 65535) return PXB_ERR_UNSUPPORTED;
     static const GaussWin gw = make_window();
     const dim3 grid((W + kLT - 1) / kLT, (H + kLT - 1) / kLT, B * C);
-    l1_ssim_bwd_kernel<<<grid, kLThreads, 0, (cudaStream_t)stream>>>(C, H, W, pred, gt, dmaps, (size_t)B * C * H * W,
-                                                                    g_l1, g_ssim, g_stride, s_l1, s_ssim, d_pred, gw);
+    PXB_CUDA_OK(launch_k(l1_ssim_bwd_kernel, grid, dim3(kLThreads), 0, (cudaStream_t)stream, C, H, W, pred, gt, dmaps,
+                         (size_t)B * C * H * W, g_l1, g_ssim, g_stride, s_l1, s_ssim, d_pred, gw));
     return (int)cudaGetLastError();
 }
 

@@ -546,6 +546,7 @@ fused_bwd_kernel(int P, const float* __restrict__ pos, const float* __restrict__
                  float* __restrict__ d_scales, float4* __restrict__ d_quats, float* __restrict__ d_opacity,
                  float* __restrict__ d_shs, float* __restrict__ d_rgb /*[P,3] or null*/, float* __restrict__ d_extra,
                  float* __restrict__ d_ndc, float* __restrict__ d_cam /*[19]: intr4, extr12, center3 or null*/) {
+    pdl_wait();
     extern __shared__ __align__(16) float sh_smem[];
     __shared__ float red[19 * (kFThreads / 32)];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -941,11 +942,10 @@ int pxb_fused_backward(int P, int sh_degree, const float* pos, const float* scal
     cudaStream_t s = (cudaStream_t)stream;
     const int nb = blocks_for(P, kFThreads);
     const size_t smem = (size_t)kFThreads * kShPitch * sizeof(float);
-#define PXB_LAUNCH_BWD(KA)                                                                                       \
-    fused_bwd_kernel<KA><<<nb, kFThreads, smem, s>>>(P, pos, scales, (const float4*)quats, shs, n_extra,         \
-                                                     with_depth, intr, extr, cam_center, W, H, S, depth, radius, \
-                                                     grec, d_pos, d_scales, (float4*)d_quats, d_opacity, d_shs,  \
-                                                     d_rgb, d_extra, d_ndc, d_cam)
+#define PXB_LAUNCH_BWD(KA)                                                                                             \
+    PXB_CUDA_OK(launch_k(fused_bwd_kernel<KA>, dim3(nb), dim3(kFThreads), smem, s, P, pos, scales, (const float4*)quats,  \
+                         shs, n_extra, with_depth, intr, extr, cam_center, W, H, S, depth, radius, grec, d_pos, d_scales, \
+                         (float4*)d_quats, d_opacity, d_shs, d_rgb, d_extra, d_ndc, d_cam))
     switch (sh_degree) {
         case 0: PXB_LAUNCH_BWD(1); break;
         case 1: PXB_LAUNCH_BWD(4); break;
