@@ -506,6 +506,23 @@ def _main(out_f):
     DEBUG_MARKS = os.environ.get("PXB_BENCH_STEP_MARKS") == "1"   # developer knobs (timeline of the timed pass)
     if rank == 0 and os.environ.get("PXB_BENCH_SAMPLER", "1") == "1":
         sampler.start()  # before the warm-up: the sampler's own start-up must not overlap the timed region
+    # Untimed settling phase before the W warm-up steps: the process has spent seconds on the host building the
+    # scene, the GPU has idled meanwhile, and on a fresh box the first few hundred milliseconds of steps also
+    # page code in.  Measured: with only W = 5 warm-up steps (10 ms of GPU work) the timed region that followed
+    # occasionally contained a 10-160 ms stall that the second pass over the same steps never showed.  So the
+    # step runs continuously for PREWARM_S seconds of wall clock first (every rank the same number of steps).
+    PREWARM_S = float(os.environ.get("PXB_BENCH_PREWARM_S", "0.6"))
+    n_pre = 0
+    t_pre = time.perf_counter()
+    while PREWARM_S > 0:
+        for _ in range(16):
+            step_fn(n_pre)
+            n_pre += 1
+        stop = torch.tensor([1.0 if time.perf_counter() - t_pre >= PREWARM_S else 0.0], device=dev)
+        if world > 1:
+            dist.all_reduce(stop, op=dist.ReduceOp.MAX)  # every rank leaves after the same number of steps
+        if stop.item() > 0:
+            break
     for s in range(W_):
         step_fn(s)
     sync()
@@ -556,7 +573,7 @@ def _main(out_f):
         "config": {"workload": workload_name(cfg, mode, c),
                    "parallelism": f"view-sharded dp{world}" + (f", gradients of 59+2 floats/Gaussian summed + max(radii) per step: {exch_kind}" if (world > 1 and train) else (", no collective (inference)" if world > 1 else "")),
                    "cache": "inputs larger than L2 (236 MB Gaussian table + records vs 126 MB L2); a different view every step"},
-        "gpu_launches": launches, "clocks": clocks,
+        "gpu_launches": launches, "clocks": clocks, "untimed_settling_steps": n_pre,
     }
 
     def finish():

@@ -104,18 +104,12 @@ int pxb_pack_records(int P, const float* uv, const float* conic, const float* op
                      int c0, int cn, int S, float* rec, void* stream);
 int pxb_unpack_grads(int P, const float* grec, int S, int C, int c0, int cn, int accumulate, float* dL_duv,
                      float* dL_dconic, float* dL_dopacity, float* dL_dfeature, void* stream);
-/* out[C,H,W], final_T[H,W], ncontrib[H,W] i32.
- * tile_order[tiles] i32 (nullable): the order in which the CTAs take the tiles -- pxb_tile_order fills it with
- * the tile ids by descending list length, so the tail of the grid is made of short tiles; NULL = raster order.
- * It changes scheduling only, never a result. */
-int pxb_blend_forward(const float* rec, int S, int C, const int* idx_sorted, const int* tile_range,
-                      const int* tile_order, float bg, int W, int H, float* final_T, int* ncontrib, float* out,
-                      void* stream);
-int pxb_blend_backward(const float* rec, int S, int C, const int* idx_sorted, const int* tile_range,
-                       const int* tile_order, float bg, int W, int H, const float* final_T, const int* ncontrib,
-                       const float* dL_dout, float* grec, void* stream);
-/* tile_order[tiles] = tile ids sorted by descending tile_range length (bucketed by 32; ties in any order). */
-int pxb_tile_order(int W, int H, const int* tile_range, int* tile_order, void* stream);
+/* out[C,H,W], final_T[H,W], ncontrib[H,W] i32 */
+int pxb_blend_forward(const float* rec, int S, int C, const int* idx_sorted, const int* tile_range, float bg, int W,
+                      int H, float* final_T, int* ncontrib, float* out, void* stream);
+int pxb_blend_backward(const float* rec, int S, int C, const int* idx_sorted, const int* tile_range, float bg, int W,
+                       int H, const float* final_T, const int* ncontrib, const float* dL_dout, float* grec,
+                       void* stream);
 /* Measurement aid (no reference counterpart): counters_dev = device pointer to >= 2 uint64 words, or NULL to
  * switch counting off.  While set, slot 0 / slot 1 accumulate the (8x4 pixel block, Gaussian) candidates the
  * warps of blend forward / backward launches executed (32 pixel-Gaussian pair tests each). */
@@ -152,9 +146,8 @@ int pxb_render_forward(int P, int sh_degree, const float* pos, const float* scal
                        const float* opacity, const float* shs, const float* extra, int n_extra, int with_depth,
                        const float* intr, const float* extr, const float* cam_center, int W, int H, float nearest,
                        float extent, float bg, int S, long long N_cap, float* rec, float* depth, int* radius,
-                       int* idx_sorted, int* tile_range, int* tile_order /*[tiles] or NULL: raster order*/, float* final_T,
-                       int* ncontrib, float* out, int* total_host, void* ws, size_t ws_bytes, void* const* stage_events,
-                       void* stream);
+                       int* idx_sorted, int* tile_range, float* final_T, int* ncontrib, float* out, int* total_host,
+                       void* ws, size_t ws_bytes, void* const* stage_events, void* stream);
 /* grec[P,S]: scratch (zeroed inside); d_cam[19] or NULL (zeroed inside); stage_events: NULL or 3 events
  * (before blend backward, between, after the per-Gaussian backward).
  * d_rgb: NULL, or [P,3] receiving the clamp-gated dL/drgb INSTEAD of d_shs (which may then be NULL): the
@@ -163,10 +156,10 @@ int pxb_render_forward(int P, int sh_degree, const float* pos, const float* scal
 int pxb_render_backward(int P, int sh_degree, const float* pos, const float* scales, const float* quats,
                         const float* shs, int n_extra, int with_depth, const float* intr, const float* extr,
                         const float* cam_center, int W, int H, float bg, int S, const float* rec, const float* depth,
-                        const int* radius, const int* idx_sorted, const int* tile_range, const int* tile_order,
-                        const float* final_T, const int* ncontrib, const float* dL_dout, float* grec, float* d_pos,
-                        float* d_scales, float* d_quats, float* d_opacity, float* d_shs, float* d_rgb, float* d_extra,
-                        float* d_ndc, float* d_cam, void* const* stage_events, void* stream);
+                        const int* radius, const int* idx_sorted, const int* tile_range, const float* final_T,
+                        const int* ncontrib, const float* dL_dout, float* grec, float* d_pos, float* d_scales,
+                        float* d_quats, float* d_opacity, float* d_shs, float* d_rgb, float* d_extra, float* d_ndc,
+                        float* d_cam, void* const* stage_events, void* stream);
 
 /* ---- data-parallel gradient exchange (all-reduce(SUM) of the parameter gradients and
  *      ndc.grad, all-reduce(MAX) of radii; the reference's equivalent is batch_size = world on one GPU,

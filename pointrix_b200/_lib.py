@@ -37,15 +37,14 @@ SIGNATURES = {
     "pxb_record_stride": (i32, [i32]),
     "pxb_pack_records": (i32, [i32, p, p, p, p, i32, i32, i32, i32, p, p]),
     "pxb_unpack_grads": (i32, [i32, p, i32, i32, i32, i32, i32, p, p, p, p, p]),
-    "pxb_blend_forward": (i32, [p, i32, i32, p, p, p, f32, i32, i32, p, p, p, p]),
-    "pxb_blend_backward": (i32, [p, i32, i32, p, p, p, f32, i32, i32, p, p, p, p, p]),
-    "pxb_tile_order": (i32, [i32, i32, p, p, p]),
+    "pxb_blend_forward": (i32, [p, i32, i32, p, p, f32, i32, i32, p, p, p, p]),
+    "pxb_blend_backward": (i32, [p, i32, i32, p, p, f32, i32, i32, p, p, p, p, p]),
     "pxb_blend_counters": (i32, [p]),
     "pxb_fused_forward": (i32, [i32, i32, p, p, p, p, p, p, i32, i32, p, p, p, i32, i32, f32, f32, i32, i32, p, p, p, p, p]),
     "pxb_render_workspace_bytes": (sz, [i32, i64, i32, i32]),
     "pxb_render_forward": (i32, [i32, i32, p, p, p, p, p, p, i32, i32, p, p, p, i32, i32, f32, f32, f32, i32, i64,
-                                 p, p, p, p, p, p, p, p, p, p, p, sz, p, p]),
-    "pxb_render_backward": (i32, [i32, i32, p, p, p, p, i32, i32, p, p, p, i32, i32, f32, i32, p, p, p, p, p, p, p, p,
+                                 p, p, p, p, p, p, p, p, p, p, sz, p, p]),
+    "pxb_render_backward": (i32, [i32, i32, p, p, p, p, i32, i32, p, p, p, i32, i32, f32, i32, p, p, p, p, p, p, p,
                                   p, p, p, p, p, p, p, p, p, p, p, p, p]),
     "pxb_nvls_allreduce": (i32, [p, i64, i64, i32, i32, p]),
     "pxb_p2p_allreduce": (i32, [p, i64, i64, i32, i32, p]),
@@ -97,7 +96,7 @@ KERNELS_PER_CALL = {
     "pxb_project_point_forward": 1, "pxb_project_point_backward": 1, "pxb_compute_cov3d_forward": 1,
     "pxb_compute_cov3d_backward": 1, "pxb_ewa_project_forward": 1, "pxb_ewa_project_backward": 1,
     "pxb_compute_sh_forward": 1, "pxb_compute_sh_backward": 1, "pxb_bin_prepare": 11, "pxb_sort_gaussian": 8,
-    "pxb_pack_records": 1, "pxb_unpack_grads": 1, "pxb_blend_forward": 1, "pxb_blend_backward": 1, "pxb_tile_order": 1,
+    "pxb_pack_records": 1, "pxb_unpack_grads": 1, "pxb_blend_forward": 1, "pxb_blend_backward": 1,
     "pxb_fused_forward": 1, "pxb_fused_backward": 1,
     "pxb_l1_ssim_forward": 2, "pxb_l1_ssim_loss_forward": 2, "pxb_l1_ssim_backward": 1, "pxb_pixel_loss_forward": 2, "pxb_pixel_loss_backward": 1,
 }
@@ -144,8 +143,8 @@ def _sort_kernels(W: int, H: int) -> int:
 def count_launches(name: str, W: int, H: int) -> None:
     """Launch accounting of the whole-view entry points (called by the renderer)."""
     global launch_count
-    # forward: fused per-Gaussian kernel, compaction + 4 x (scan, scatter), key emission + tile passes + ranges, tile order, blend
-    n = (1 + 9 + _sort_kernels(W, H) + 1 + 1) if name == "pxb_render_forward" else 2
+    # forward: fused per-Gaussian kernel, compaction + 4 x (scan, scatter), key emission + tile passes + ranges, blend
+    n = (1 + 9 + _sort_kernels(W, H) + 1) if name == "pxb_render_forward" else 2
     launch_count += n
     if _timer is not None:
         _timer.launches += n

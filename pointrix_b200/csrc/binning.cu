@@ -570,43 +570,6 @@ __global__ void rebuild_keys_kernel(int N, const unsigned int* __restrict__ tile
     keys[i] = ((long long)tile_sorted[i] << 32) | (long long)(int)__float_as_uint(depth[idx_sorted[i]]);
 }
 
-// Heaviest tiles first.  The blend kernels take one 16x16 tile per CTA and a tile's cost follows its list length
-// (a few up to several thousand entries): in raster order the last wave of the grid holds arbitrary tiles and
-// the SMs idle behind the longest of them.  One CTA buckets the tiles by list length (32 entries per bucket,
-// 256 buckets) and lays the buckets out longest first; the order inside a bucket does not matter.
-__global__ void __launch_bounds__(1024)
-tile_order_kernel(int num_tiles, const int2* __restrict__ tile_range, int* __restrict__ order) {
-    pdl_wait();
-    __shared__ int s_cnt[256], s_base[256];
-    const int tid = threadIdx.x;
-    if (tid < 256) s_cnt[tid] = 0;
-    __syncthreads();
-    for (int t = tid; t < num_tiles; t += 1024) {
-        const int2 r = tile_range[t];
-        atomicAdd(&s_cnt[255 - min((r.y - r.x) >> 5, 255)], 1);  // bucket 0 = the longest lists
-    }
-    __syncthreads();
-    if (tid < 32) {  // exclusive scan of the 256 bucket sizes by one warp, 8 buckets per lane
-        int v[8], sum = 0;
-#pragma unroll
-        for (int k = 0; k < 8; k++) { v[k] = s_cnt[tid * 8 + k]; sum += v[k]; }
-        int incl = sum;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int n = __shfl_up_sync(0xffffffffu, incl, o);
-            if (tid >= o) incl += n;
-        }
-        int run = incl - sum;
-#pragma unroll
-        for (int k = 0; k < 8; k++) { s_base[tid * 8 + k] = run; run += v[k]; }
-    }
-    __syncthreads();
-    for (int t = tid; t < num_tiles; t += 1024) {
-        const int2 r = tile_range[t];
-        order[atomicAdd(&s_base[255 - min((r.y - r.x) >> 5, 255)], 1)] = t;
-    }
-}
-
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 static inline int ceil_log2(int x) {
     int b = 0;
@@ -805,13 +768,6 @@ int pxb::sort_gaussian(int P, long long N, int* total_dev, int publish, int* tot
     if (keys_sorted_out && total_dev == nullptr)
         rebuild_keys_kernel<<<(int)((N + 255) / 256), 256, 0, s>>>((int)N, tile_sorted, idx_sorted, depth, keys_sorted_out);
     return (int)cudaGetLastError();
-}
-
-extern "C" int pxb_tile_order(int W, int H, const int* tile_range, int* tile_order, void* stream) {
-    const int gx = (W + PXB_TILE - 1) / PXB_TILE, gy = (H + PXB_TILE - 1) / PXB_TILE;
-    if (gx * gy <= 0) return 0;
-    return (int)launch_k(tile_order_kernel, dim3(1), dim3(1024), 0, (cudaStream_t)stream, gx * gy, (const int2*)tile_range,
-                         tile_order);
 }
 
 extern "C" int pxb_sort_gaussian(int P, long long N, const int* total_dev, const float* uv, int uv_stride, int tight,

@@ -110,6 +110,24 @@ __device__ __forceinline__ unsigned int opaque_u32(unsigned int x) {
     asm volatile("mov.u32 %0, %1;" : "=r"(y) : "r"(x));
     return y;
 }
+__device__ __forceinline__ float2 lds64(unsigned int a) {
+    float2 v;
+    asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ float lds32(unsigned int a) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ int lds32i(unsigned int a) {
+    int v;
+    asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts64(unsigned int a, float x, float y) {
+    asm volatile("st.shared.v2.f32 [%0], {%1,%2};" ::"r"(a), "f"(x), "f"(y) : "memory");
+}
 __device__ __forceinline__ unsigned int lds_u16(unsigned int a) {
     unsigned short v;
     asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a) : "memory");
@@ -175,8 +193,8 @@ __device__ __forceinline__ void bulk_g2s(unsigned int dst, const void* src, unsi
 template <int CH, int S, bool BULK>
 __global__ void __launch_bounds__(kBlendThreads)
 blend_fwd_kernel(const float* __restrict__ rec, const int* __restrict__ idx_sorted, const int2* __restrict__ tile_range,
-                 const int* __restrict__ tile_order, float bg, int C, int W, int H, int gx, float* __restrict__ final_T,
-                 int* __restrict__ ncontrib, float* __restrict__ out) {
+                 float bg, int C, int W, int H, int gx, float* __restrict__ final_T, int* __restrict__ ncontrib,
+                 float* __restrict__ out) {
     pdl_wait();
     constexpr int NBUF = BULK ? 2 : 1;
     extern __shared__ __align__(16) float sm_f[];
@@ -184,10 +202,10 @@ blend_fwd_kernel(const float* __restrict__ rec, const int* __restrict__ idx_sort
     unsigned short* sm_list = reinterpret_cast<unsigned short*>(sm_f + NBUF * (kBatch + 1) * S);  // [8 warps][kBatch + kUnroll]
     unsigned char* sm_mask = reinterpret_cast<unsigned char*>(sm_list + (kBlendThreads / 32) * (kBatch + kUnroll));
     __shared__ __align__(8) unsigned long long s_bar[2];
-    // heaviest tiles first (tile_order: tile ids by descending list length): the tail of the grid is made of
-    // short tiles instead of whatever the raster order ends with
-    const int tile = tile_order ? tile_order[blockIdx.x] : (int)blockIdx.x;
-    const int tx = tile % gx, ty = tile / gx;
+    // (taking the tiles heaviest-first instead of in raster order was measured: no gain, the dynamic CTA
+    // scheduler already leaves a tail shorter than one tile)
+    const int tile = blockIdx.y * gx + blockIdx.x;
+    const int tx = blockIdx.x, ty = blockIdx.y;
     int lx, ly;
     thread_pixel(lx, ly);
     const int pxi = tx * PXB_TILE + lx, pyi = ty * PXB_TILE + ly;
@@ -327,12 +345,11 @@ blend_fwd_kernel(const float* __restrict__ rec, const int* __restrict__ idx_sort
 constexpr int kSlots = 16;
 constexpr int kSlotPitch = 33;  // float2 units: conflict-free row (phase 1) and column (phase 2) access
 
-template <int CH, int S>
-__global__ void __launch_bounds__(kBlendThreads, (CH <= 4 ? 4 : 1))
+template <int CH, int S, int MINB>  // MINB: resident CTAs per SM the register allocation aims for
+__global__ void __launch_bounds__(kBlendThreads, MINB)
 blend_bwd_kernel(const float* __restrict__ rec, const int* __restrict__ idx_sorted, const int2* __restrict__ tile_range,
-                 const int* __restrict__ tile_order, float bg, int C, int W, int H, int gx,
-                 const float* __restrict__ final_T, const int* __restrict__ ncontrib, const float* __restrict__ dL_dout,
-                 float* __restrict__ grec) {
+                 float bg, int C, int W, int H, int gx, const float* __restrict__ final_T,
+                 const int* __restrict__ ncontrib, const float* __restrict__ dL_dout, float* __restrict__ grec) {
     pdl_wait();
     constexpr int CHP = (CH + 3) & ~3;  // dL/dpix row padded to float4s
     constexpr int NW = kBlendThreads / 32;
@@ -343,8 +360,8 @@ blend_bwd_kernel(const float* __restrict__ rec, const int* __restrict__ idx_sort
     int* sm_id = reinterpret_cast<int*>(sm_slot + NW * kSlots * kSlotPitch);  // [kBatch]
     unsigned short* sm_list = reinterpret_cast<unsigned short*>(sm_id + kBatch);  // [NW][kBatch]
     unsigned char* sm_mask = reinterpret_cast<unsigned char*>(sm_list + NW * kBatch);  // [kBatch]
-    const int tile = tile_order ? tile_order[blockIdx.x] : (int)blockIdx.x;  // heaviest tiles first, as the forward
-    const int tx = tile % gx, ty = tile / gx;
+    const int tile = blockIdx.y * gx + blockIdx.x;
+    const int tx = blockIdx.x, ty = blockIdx.y;
     int lx, ly;
     thread_pixel(lx, ly);
     const int pxi = tx * PXB_TILE + lx, pyi = ty * PXB_TILE + ly;
@@ -390,34 +407,49 @@ blend_bwd_kernel(const float* __restrict__ rec, const int* __restrict__ idx_sort
     const unsigned int rec_s = opaque_u32((unsigned int)__cvta_generic_to_shared(sm_rec));
     const unsigned int list_s = opaque_u32((unsigned int)__cvta_generic_to_shared(my_list));
 
+    // every shared-memory access of the hot path goes through a 32-bit shared address held in a register
+    // (generic pointers made the compiler rebuild the shared window base inside the loops)
+    const unsigned int slot_s = opaque_u32((unsigned int)__cvta_generic_to_shared(slots));            // this warp's slots
+    const unsigned int slot_w = slot_s + 8u * lane;                                                    // phase 1: my column
+    const unsigned int slot_r = slot_s + 8u * (unsigned)(my_slot * kSlotPitch + 16 * my_half);         // phase 2: my half row
+    const unsigned int dpix_r = opaque_u32((unsigned int)__cvta_generic_to_shared(wdpix + 16 * my_half * CHP));
+    const unsigned int id_s = opaque_u32((unsigned int)__cvta_generic_to_shared(sm_id));
+    unsigned int slot_cur = slot_w;  // advances by one slot row per parked Gaussian
+
     auto flush = [&](int n) {
         __syncwarp();
-        const float* r = sm_rec + my_j * S;
-        const float4 r0 = *reinterpret_cast<const float4*>(r);      // u v A B
-        const float2 r1 = *reinterpret_cast<const float2*>(r + 4);  // C op
-        const float ub = r0.x - bx, vb = r0.y - by;
-        float Q0 = 0.f, Q1 = 0.f, Q2 = 0.f, Q3 = 0.f, Q4 = 0.f, Q5 = 0.f;
+        const unsigned int ra = rec_s + (unsigned)my_j * (S * 4u);
+        const float4 r0 = lds128(ra);       // u v A B
+        const float2 r1 = lds64(ra + 16u);  // C op
+        // moments of q over this lane's 16 pixels in block-local pixel coordinates x = i & 7, y = i >> 3
+        // (compile-time constants: one FFMA each), shifted to the Gaussian's centre afterwards
+        float M0 = 0.f, Mx = 0.f, My = 0.f, Mxx = 0.f, Mxy = 0.f, Myy = 0.f;
         float Fk[CH];
 #pragma unroll
         for (int k = 0; k < CH; k++) Fk[k] = 0.f;
-        const float2* row = slots + my_slot * kSlotPitch + 16 * my_half;
-        const float* dp = wdpix + 16 * my_half * CHP;
 #pragma unroll
         for (int i = 0; i < 16; i++) {
-            const float2 qw = row[i];
-            const float dx = ub - (float)(i & 7), dy = vb - (float)(i >> 3);
-            const float qdx = qw.x * dx, qdy = qw.x * dy;
-            Q0 += qw.x; Q1 += qdx; Q2 += qdy;
-            Q3 = fmaf(qdx, dx, Q3); Q4 = fmaf(qdx, dy, Q4); Q5 = fmaf(qdy, dy, Q5);
+            const float2 qw = lds64(slot_r + 8u * i);
+            const float x = (float)(i & 7), y = (float)(i >> 3);
+            M0 += qw.x;
+            Mx = fmaf(qw.x, x, Mx); My = fmaf(qw.x, y, My);
+            Mxx = fmaf(qw.x, x * x, Mxx); Mxy = fmaf(qw.x, x * y, Mxy); Myy = fmaf(qw.x, y * y, Myy);
 #pragma unroll
             for (int k4 = 0; k4 < CHP; k4 += 4) {
-                const float4 d4 = *reinterpret_cast<const float4*>(dp + i * CHP + k4);
+                const float4 d4 = lds128(dpix_r + 4u * (i * CHP + k4));
                 Fk[k4] = fmaf(qw.y, d4.x, Fk[k4]);
                 if (k4 + 1 < CH) Fk[k4 + 1] = fmaf(qw.y, d4.y, Fk[k4 + 1]);
                 if (k4 + 2 < CH) Fk[k4 + 2] = fmaf(qw.y, d4.z, Fk[k4 + 2]);
                 if (k4 + 3 < CH) Fk[k4 + 3] = fmaf(qw.y, d4.w, Fk[k4 + 3]);
             }
         }
+        // dx = ub - x, dy = vb - y with (ub, vb) the centre relative to this half block's origin
+        const float ub = r0.x - bx, vb = r0.y - by;
+        float Q0 = M0;
+        float Q1 = fmaf(ub, M0, -Mx), Q2 = fmaf(vb, M0, -My);
+        float Q3 = fmaf(ub, fmaf(ub, M0, -2.f * Mx), Mxx);
+        float Q4 = fmaf(ub, fmaf(vb, M0, -My), fmaf(-vb, Mx, Mxy));
+        float Q5 = fmaf(vb, fmaf(vb, M0, -2.f * My), Myy);
         Q0 += __shfl_xor_sync(0xffffffffu, Q0, 16); Q1 += __shfl_xor_sync(0xffffffffu, Q1, 16);
         Q2 += __shfl_xor_sync(0xffffffffu, Q2, 16); Q3 += __shfl_xor_sync(0xffffffffu, Q3, 16);
         Q4 += __shfl_xor_sync(0xffffffffu, Q4, 16); Q5 += __shfl_xor_sync(0xffffffffu, Q5, 16);
@@ -434,7 +466,7 @@ blend_bwd_kernel(const float* __restrict__ rec, const int* __restrict__ idx_sort
             g[5] = Q0;
 #pragma unroll
             for (int k = 0; k < S - 6; k++) g[6 + k] = (k < CH) ? Fk[k] : 0.f;
-            float* dst = grec + (size_t)sm_id[my_j] * S;
+            float* dst = grec + (size_t)lds32i(id_s + 4u * (unsigned)my_j) * S;
 #pragma unroll
             for (int q4 = 0; q4 < S; q4 += 4) {
                 if (q4 + 1 >= 6 + CH) {          // one live value left in this float4
@@ -444,6 +476,7 @@ blend_bwd_kernel(const float* __restrict__ rec, const int* __restrict__ idx_sort
                 }
             }
         }
+        slot_cur = slot_w;
         __syncwarp();
     };
 
@@ -487,10 +520,14 @@ blend_bwd_kernel(const float* __restrict__ rec, const int* __restrict__ idx_sort
             const float G = blend_G(power);
             const float alpha = fmin_nn(__fmul_rn(r1.y, G), 0.99f);
             const bool valid = pos < last && power <= 0.f && alpha >= 1.0f / 255.0f;
+#ifdef PXB_STATS
             const unsigned int vm = __ballot_sync(0xffffffffu, valid);
             if (vm == 0u) continue;
             PXB_STAT(1, 1); PXB_STAT(2, __popc(vm));
-            float2 qw = make_float2(0.f, 0.f);
+#else
+            if (!__any_sync(0xffffffffu, valid)) continue;
+#endif
+            float qx = 0.f, qy = 0.f;
             if (valid) {
                 // dL/dalpha = T * <f - accum, dpix> - T_final/(1-alpha) * bg * sum(dpix)   (alpha_blending.cu:206-222)
                 // with accum the normalised colour behind this Gaussian.  Only dot products with the
@@ -499,16 +536,17 @@ blend_bwd_kernel(const float* __restrict__ rec, const int* __restrict__ idx_sort
                 //   dL/dalpha = T <f, dpix> - B / (1 - alpha).
                 const float ra1 = __fdividef(1.f, 1.f - alpha);
                 T = T * ra1;
-                qw.y = alpha * T;
+                qy = alpha * T;
                 float fd = r1.z * dpix[0];
                 if (CH > 1) fd = fmaf(r1.w, dpix[1], fd);
 #pragma unroll
-                for (int k = 2; k < CH; k++) fd = fmaf(sm_rec[j * S + 6 + k], dpix[k], fd);
+                for (int k = 2; k < CH; k++) fd = fmaf(lds32(ra + 4u * (6 + k)), dpix[k], fd);
                 const float dL_dalpha = fmaf(T, fd, -(ra1 * Bacc));
-                Bacc = fmaf(qw.y, fd, Bacc);
-                qw.x = G * dL_dalpha;
+                Bacc = fmaf(qy, fd, Bacc);
+                qx = G * dL_dalpha;
             }
-            slots[nslot * kSlotPitch + lane] = qw;
+            sts64(slot_cur, qx, qy);
+            slot_cur += 8u * kSlotPitch;
             if (my_slot == nslot) my_j = j;
             nslot++;
             if (nslot == kSlots) {
@@ -568,7 +606,7 @@ static bool bulk_staging() {
 }
 
 template <int CH, int S, bool BULK>
-static int launch_fwd_v(const float* rec, const int* idx_sorted, const int* tile_range, const int* tile_order, float bg,
+static int launch_fwd_v(const float* rec, const int* idx_sorted, const int* tile_range, float bg,
                         int C, int W, int H, float* final_T, int* ncontrib, float* out, cudaStream_t s) {
     const int gx = (W + PXB_TILE - 1) / PXB_TILE, gy = (H + PXB_TILE - 1) / PXB_TILE;
     const size_t smem = (size_t)(BULK ? 2 : 1) * (kBatch + 1) * S * 4 + (kBlendThreads / 32) * (kBatch + kUnroll) * 2 + kBatch;
@@ -580,37 +618,55 @@ static int launch_fwd_v(const float* rec, const int* idx_sorted, const int* tile
                                          cudaSharedmemCarveoutMaxShared));
         attr = true;
     }
-    PXB_CUDA_OK(launch_k(blend_fwd_kernel<CH, S, BULK>, dim3(gx * gy), dim3(kBlendThreads), smem, s, rec, idx_sorted,
-                         (const int2*)tile_range, tile_order, bg, C, W, H, gx, final_T, ncontrib, out));
+    PXB_CUDA_OK(launch_k(blend_fwd_kernel<CH, S, BULK>, dim3(gx, gy), dim3(kBlendThreads), smem, s, rec, idx_sorted,
+                         (const int2*)tile_range, bg, C, W, H, gx, final_T, ncontrib, out));
     return (int)cudaGetLastError();
 }
 
 template <int CH, int S>
-static int launch_fwd(const float* rec, const int* idx_sorted, const int* tile_range, const int* tile_order, float bg, int C,
+static int launch_fwd(const float* rec, const int* idx_sorted, const int* tile_range, float bg, int C,
                       int W, int H, float* final_T, int* ncontrib, float* out, cudaStream_t s) {
     if (bulk_staging() && S <= 16)  // two staging buffers: the wide strides keep the single-buffer variant
-        return launch_fwd_v<CH, S, true>(rec, idx_sorted, tile_range, tile_order, bg, C, W, H, final_T, ncontrib, out, s);
-    return launch_fwd_v<CH, S, false>(rec, idx_sorted, tile_range, tile_order, bg, C, W, H, final_T, ncontrib, out, s);
+        return launch_fwd_v<CH, S, true>(rec, idx_sorted, tile_range, bg, C, W, H, final_T, ncontrib, out, s);
+    return launch_fwd_v<CH, S, false>(rec, idx_sorted, tile_range, bg, C, W, H, final_T, ncontrib, out, s);
 }
 
-template <int CH, int S>
-static int launch_bwd(const float* rec, const int* idx_sorted, const int* tile_range, const int* tile_order, float bg, int C,
-                      int W, int H, const float* final_T, const int* ncontrib, const float* dL_dout, float* grec,
-                      cudaStream_t s) {
+// C <= 4: 3 CTAs per SM with 80 registers (no spills, no re-materialised addresses in the pair loop) or 4 CTAs
+// with 64 (PXB_BWD_OCC=4); measured on cfg4, see DESIGN.md section 4
+static int bwd_occupancy() {
+    static const int v = [] {
+        const char* e = getenv("PXB_BWD_OCC");
+        return (e && e[0] == '4') ? 4 : 3;
+    }();
+    return v;
+}
+
+template <int CH, int S, int MINB>
+static int launch_bwd_v(const float* rec, const int* idx_sorted, const int* tile_range, float bg, int C, int W, int H,
+                        const float* final_T, const int* ncontrib, const float* dL_dout, float* grec, cudaStream_t s) {
     const int gx = (W + PXB_TILE - 1) / PXB_TILE, gy = (H + PXB_TILE - 1) / PXB_TILE;
     constexpr int CHP = (CH + 3) & ~3, NW = kBlendThreads / 32;
     const size_t smem = (size_t)(kBatch * S + NW * 32 * CHP + 2 * NW * kSlots * kSlotPitch) * 4 + kBatch * 4 + NW * kBatch * 2 + kBatch;
     static bool attr = false;
     if (!attr) {
         if (smem > 48 * 1024)
-            PXB_CUDA_OK(cudaFuncSetAttribute(blend_bwd_kernel<CH, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        PXB_CUDA_OK(cudaFuncSetAttribute(blend_bwd_kernel<CH, S>, cudaFuncAttributePreferredSharedMemoryCarveout,
+            PXB_CUDA_OK(cudaFuncSetAttribute(blend_bwd_kernel<CH, S, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        PXB_CUDA_OK(cudaFuncSetAttribute(blend_bwd_kernel<CH, S, MINB>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                          cudaSharedmemCarveoutMaxShared));
         attr = true;
     }
-    PXB_CUDA_OK(launch_k(blend_bwd_kernel<CH, S>, dim3(gx * gy), dim3(kBlendThreads), smem, s, rec, idx_sorted,
-                         (const int2*)tile_range, tile_order, bg, C, W, H, gx, final_T, ncontrib, dL_dout, grec));
+    PXB_CUDA_OK(launch_k(blend_bwd_kernel<CH, S, MINB>, dim3(gx, gy), dim3(kBlendThreads), smem, s, rec, idx_sorted,
+                         (const int2*)tile_range, bg, C, W, H, gx, final_T, ncontrib, dL_dout, grec));
     return (int)cudaGetLastError();
+}
+
+template <int CH, int S>
+static int launch_bwd(const float* rec, const int* idx_sorted, const int* tile_range, float bg, int C, int W, int H,
+                      const float* final_T, const int* ncontrib, const float* dL_dout, float* grec, cudaStream_t s) {
+    if (CH > 4) return launch_bwd_v<CH, S, 1>(rec, idx_sorted, tile_range, bg, C, W, H, final_T, ncontrib, dL_dout, grec, s);
+    if (bwd_occupancy() == 4)
+        return launch_bwd_v<CH, S, (CH <= 4 ? 4 : 1)>(rec, idx_sorted, tile_range, bg, C, W, H, final_T, ncontrib, dL_dout, grec, s);
+    return launch_bwd_v<CH, S, (CH <= 4 ? 3 : 1)>(rec, idx_sorted, tile_range, bg, C, W, H, final_T, ncontrib, dL_dout, grec, s);
 }
 
 // kernels are instantiated for the exact channel count up to 10 (rgb, rgb+depth, rgb+normal, ... the
@@ -648,24 +704,23 @@ int pxb_record_stride(int C) {
     return -1;
 }
 
-int pxb_blend_forward(const float* rec, int S, int C, const int* idx_sorted, const int* tile_range,
-                      const int* tile_order, float bg, int W, int H, float* final_T, int* ncontrib, float* out,
-                      void* stream) {
+int pxb_blend_forward(const float* rec, int S, int C, const int* idx_sorted, const int* tile_range, float bg, int W,
+                      int H, float* final_T, int* ncontrib, float* out, void* stream) {
     cudaStream_t s = (cudaStream_t)stream;
     if (W <= 0 || H <= 0) return 0;
     if (C < 1 || C > PXB_MAX_CHANNELS_PER_PASS || S != pxb_record_stride(C)) return PXB_ERR_BAD_ARG;
     if (((uintptr_t)rec) & 15) return PXB_ERR_ALIGN;
-    PXB_BLEND_DISPATCH(launch_fwd, rec, idx_sorted, tile_range, tile_order, bg, C, W, H, final_T, ncontrib, out, s)
+    PXB_BLEND_DISPATCH(launch_fwd, rec, idx_sorted, tile_range, bg, C, W, H, final_T, ncontrib, out, s)
 }
 
-int pxb_blend_backward(const float* rec, int S, int C, const int* idx_sorted, const int* tile_range,
-                       const int* tile_order, float bg, int W, int H, const float* final_T, const int* ncontrib,
-                       const float* dL_dout, float* grec, void* stream) {
+int pxb_blend_backward(const float* rec, int S, int C, const int* idx_sorted, const int* tile_range, float bg, int W,
+                       int H, const float* final_T, const int* ncontrib, const float* dL_dout, float* grec,
+                       void* stream) {
     cudaStream_t s = (cudaStream_t)stream;
     if (W <= 0 || H <= 0) return 0;
     if (C < 1 || C > PXB_MAX_CHANNELS_PER_PASS || S != pxb_record_stride(C)) return PXB_ERR_BAD_ARG;
     if ((((uintptr_t)rec) | ((uintptr_t)grec)) & 15) return PXB_ERR_ALIGN;
-    PXB_BLEND_DISPATCH(launch_bwd, rec, idx_sorted, tile_range, tile_order, bg, C, W, H, final_T, ncontrib, dL_dout, grec, s)
+    PXB_BLEND_DISPATCH(launch_bwd, rec, idx_sorted, tile_range, bg, C, W, H, final_T, ncontrib, dL_dout, grec, s)
 }
 
 // counters: device pointer to >= 2 unsigned 64-bit words (NULL switches counting off).  Slot 0 accumulates

@@ -61,8 +61,8 @@ int pxb_render_forward(int P, int sh_degree, const float* pos, const float* scal
                        const float* opacity, const float* shs, const float* extra, int n_extra, int with_depth,
                        const float* intr, const float* extr, const float* cam_center, int W, int H, float nearest,
                        float extent, float bg, int S, long long N_cap, float* rec, float* depth, int* radius,
-                       int* idx_sorted, int* tile_range, int* tile_order, float* final_T, int* ncontrib, float* out,
-                       int* total_host, void* ws, size_t ws_bytes, void* const* stage_events, void* stream) {
+                       int* idx_sorted, int* tile_range, float* final_T, int* ncontrib, float* out, int* total_host,
+                       void* ws, size_t ws_bytes, void* const* stage_events, void* stream) {
     cudaStream_t s = (cudaStream_t)stream;
     const int C = 3 + (with_depth ? 1 : 0) + n_extra;
     if (P <= 0 || N_cap <= 0 || W <= 0 || H <= 0) return PXB_ERR_BAD_ARG;
@@ -85,12 +85,7 @@ int pxb_render_forward(int P, int sh_degree, const float* pos, const float* scal
                        b.tiles, W, H, idx_sorted, tile_range, nullptr, b.ws_p, b.ws_p_bytes, b.ws_n, b.ws_n_bytes, stream);
     if (rc) return rc;
     if ((rc = mark(stage_events, 3, s))) return rc;
-    const int* order = nullptr;
-    if (tile_order) {  // heaviest tiles first for both blend kernels (scheduling only)
-        if ((rc = pxb_tile_order(W, H, tile_range, tile_order, stream))) return rc;
-        order = tile_order;
-    }
-    rc = pxb_blend_forward(rec, S, C, idx_sorted, tile_range, order, bg, W, H, final_T, ncontrib, out, stream);
+    rc = pxb_blend_forward(rec, S, C, idx_sorted, tile_range, bg, W, H, final_T, ncontrib, out, stream);
     if (rc) return rc;
     return mark(stage_events, 4, s);
 }
@@ -98,8 +93,8 @@ int pxb_render_forward(int P, int sh_degree, const float* pos, const float* scal
 int pxb_render_backward(int P, int sh_degree, const float* pos, const float* scales, const float* quats,
                         const float* shs, int n_extra, int with_depth, const float* intr, const float* extr,
                         const float* cam_center, int W, int H, float bg, int S, const float* rec, const float* depth,
-                        const int* radius, const int* idx_sorted, const int* tile_range, const int* tile_order,
-                        const float* final_T, const int* ncontrib, const float* dL_dout, float* grec, float* d_pos, float* d_scales,
+                        const int* radius, const int* idx_sorted, const int* tile_range, const float* final_T,
+                        const int* ncontrib, const float* dL_dout, float* grec, float* d_pos, float* d_scales,
                         float* d_quats, float* d_opacity, float* d_shs, float* d_rgb, float* d_extra, float* d_ndc,
                         float* d_cam, void* const* stage_events, void* stream) {
     cudaStream_t s = (cudaStream_t)stream;
@@ -109,7 +104,7 @@ int pxb_render_backward(int P, int sh_degree, const float* pos, const float* sca
     PXB_CUDA_OK(cudaMemsetAsync(grec, 0, (size_t)P * S * sizeof(float), s));
     if (d_cam) PXB_CUDA_OK(cudaMemsetAsync(d_cam, 0, 19 * sizeof(float), s));
     if ((rc = mark(stage_events, 0, s))) return rc;
-    rc = pxb_blend_backward(rec, S, C, idx_sorted, tile_range, tile_order, bg, W, H, final_T, ncontrib, dL_dout, grec, stream);
+    rc = pxb_blend_backward(rec, S, C, idx_sorted, tile_range, bg, W, H, final_T, ncontrib, dL_dout, grec, stream);
     if (rc) return rc;
     if ((rc = mark(stage_events, 1, s))) return rc;
     rc = pxb_fused_backward(P, sh_degree, pos, scales, quats, shs, n_extra, with_depth, intr, extr, cam_center, W, H, S,

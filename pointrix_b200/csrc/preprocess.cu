@@ -7,6 +7,8 @@
 // All of them are HBM streams: one thread per Gaussian, inputs read once,
 // outputs written once, camera gradients reduced per block before touching
 // global atomics.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "sh.cuh"
 #include "pointrix_b200.h"
@@ -536,8 +538,8 @@ fused_fwd_kernel(int P, const float* __restrict__ pos, const float* __restrict__
 //   opacity, shs (clamp- and degree-masked), extra features
 //   ndc.grad  = duv * (W/2, H/2)                (msplat/msplat/alpha_blending.py:106-110)
 //   camera: dintr[4], dextr[12], dcam_center[3] block-reduced then atomically added.
-template <int KA>
-__global__ void __launch_bounds__(kFThreads)
+template <int KA, int MINB>  // MINB: resident CTAs per SM the register allocation aims for
+__global__ void __launch_bounds__(kFThreads, MINB)
 fused_bwd_kernel(int P, const float* __restrict__ pos, const float* __restrict__ scales,
                  const float4* __restrict__ quats, const float* __restrict__ shs, int n_extra, int with_depth,
                  const float* __restrict__ intr, const float* __restrict__ extr,
@@ -942,10 +944,15 @@ int pxb_fused_backward(int P, int sh_degree, const float* pos, const float* scal
     cudaStream_t s = (cudaStream_t)stream;
     const int nb = blocks_for(P, kFThreads);
     const size_t smem = (size_t)kFThreads * kShPitch * sizeof(float);
-#define PXB_LAUNCH_BWD(KA)                                                                                             \
-    PXB_CUDA_OK(launch_k(fused_bwd_kernel<KA>, dim3(nb), dim3(kFThreads), smem, s, P, pos, scales, (const float4*)quats,  \
-                         shs, n_extra, with_depth, intr, extr, cam_center, W, H, S, depth, radius, grec, d_pos, d_scales, \
-                         (float4*)d_quats, d_opacity, d_shs, d_rgb, d_extra, d_ndc, d_cam))
+    // 121 registers un-capped (4 CTAs of 128 threads per SM); PXB_FBWD_OCC=5 caps at 96 (5 CTAs, 52 bytes spilled)
+    static const int occ = [] { const char* e = getenv("PXB_FBWD_OCC"); return (e && e[0] == '5') ? 5 : 4; }();
+#define PXB_LAUNCH_BWD_V(KA, MINB)                                                                                      \
+    PXB_CUDA_OK(launch_k(fused_bwd_kernel<KA, MINB>, dim3(nb), dim3(kFThreads), smem, s, P, pos, scales,                  \
+                         (const float4*)quats, shs, n_extra, with_depth, intr, extr, cam_center, W, H, S, depth, radius,  \
+                         grec, d_pos, d_scales, (float4*)d_quats, d_opacity, d_shs, d_rgb, d_extra, d_ndc, d_cam))
+#define PXB_LAUNCH_BWD(KA)                    \
+    if (occ == 5) { PXB_LAUNCH_BWD_V(KA, 5); } \
+    else { PXB_LAUNCH_BWD_V(KA, 4); }
     switch (sh_degree) {
         case 0: PXB_LAUNCH_BWD(1); break;
         case 1: PXB_LAUNCH_BWD(4); break;
@@ -953,6 +960,7 @@ int pxb_fused_backward(int P, int sh_degree, const float* pos, const float* scal
         default: PXB_LAUNCH_BWD(16); break;
     }
 #undef PXB_LAUNCH_BWD
+#undef PXB_LAUNCH_BWD_V
     return (int)cudaGetLastError();
 }
 

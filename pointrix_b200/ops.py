@@ -298,7 +298,7 @@ class _AlphaBlending(torch.autograd.Function):
             for c0, cn, S in _chunks(Cc):
                 rec = torch.empty(max(P, 1), S, dtype=torch.float32, device=dev)
                 launch("pxb_pack_records", P, _p(uv_c), _p(cn_c), _p(op_c), _p(ft_c), Cc, c0, cn, S, _p(rec), stream)
-                launch("pxb_blend_forward", _p(rec), S, cn, _p(ids), _p(tr), _p(None), bg, W, H, _p(final_T), _p(ncontrib),
+                launch("pxb_blend_forward", _p(rec), S, cn, _p(ids), _p(tr), bg, W, H, _p(final_T), _p(ncontrib),
                                             _p(out[c0:]), stream)
                 if Cc <= MAX_CH:
                     rec_keep = rec
@@ -329,7 +329,7 @@ class _AlphaBlending(torch.autograd.Function):
                     rec = torch.empty(max(P, 1), S, dtype=torch.float32, device=dev)
                     launch("pxb_pack_records", P, _p(uv), _p(conic), _p(opacity), _p(feature), Cc, c0, cn, S, _p(rec), stream)
                 grec = torch.zeros(max(P, 1), S, dtype=torch.float32, device=dev)
-                launch("pxb_blend_backward", _p(rec), S, cn, _p(ids), _p(tr), _p(None), bg, W, H, _p(final_T), _p(ncontrib),
+                launch("pxb_blend_backward", _p(rec), S, cn, _p(ids), _p(tr), bg, W, H, _p(final_T), _p(ncontrib),
                                              _p(g[c0:]), _p(grec), stream)
                 launch("pxb_unpack_grads", P, _p(grec), S, Cc, c0, cn, 1 if n > 0 else 0, _p(d_uv), _p(d_conic), _p(d_op),
                                            _p(d_feat), stream)
@@ -362,7 +362,7 @@ def alpha_blending_aux(uv, conic, opacity, feature, idx_sorted, tile_range, bg, 
         for c0, cn, S in _chunks(Cc):
             rec = torch.empty(max(P, 1), S, dtype=torch.float32, device=dev)
             launch("pxb_pack_records", P, _p(uv_c), _p(cn_c), _p(op_c), _p(ft_c), Cc, c0, cn, S, _p(rec), stream)
-            launch("pxb_blend_forward", _p(rec), S, cn, _p(ids), _p(tr), _p(None), float(bg), int(W), int(H), _p(final_T),
+            launch("pxb_blend_forward", _p(rec), S, cn, _p(ids), _p(tr), float(bg), int(W), int(H), _p(final_T),
                                         _p(ncontrib), _p(out[c0:]), stream)
     return out, final_T, ncontrib
 

@@ -14,7 +14,6 @@ reference's ~14 kernels + ~40 torch ops; the autograd graph of ``render_iter``
 from __future__ import annotations
 
 import ctypes as C
-import os
 import time
 from dataclasses import dataclass
 from typing import Dict, Optional
@@ -77,7 +76,6 @@ _COUNT_WORD = {}
 _WORKSPACE = {}
 _CAPACITY = {}
 _raw_stream = torch._C._cuda_getCurrentRawStream
-_TILE_ORDER = os.environ.get("PXB_TILE_ORDER", "1") != "0"
 
 
 def _count_word(dev_index: int):
@@ -153,8 +151,6 @@ class _FusedRender(torch.autograd.Function):
         depth = E((P,), dtype=f32, device=dev)
         radius = E((P,), dtype=i32, device=dev)
         tile_range = E((n_tiles, 2), dtype=i32, device=dev)
-        # heaviest tiles first for both blend kernels (scheduling only; PXB_TILE_ORDER=0: raster order)
-        tile_order = E((n_tiles,), dtype=i32, device=dev) if _TILE_ORDER else None
         out = E((Cc, H, W), dtype=f32, device=dev)
         final_T = E((H, W), dtype=f32, device=dev)
         ncontrib = E((H, W), dtype=i32, device=dev)
@@ -177,7 +173,7 @@ class _FusedRender(torch.autograd.Function):
             word.value = -1
             args = (P, int(sh_degree), _p(pos), _p(sc), _p(rot), _p(op), _p(sh), _p(ex), n_extra, int(with_depth),
                     _p(intr_c), _p(extr_c), _p(cc), W, H, float(nearest), 1.3, float(bg), S, cap, _p(rec), _p(depth),
-                    _p(radius), _p(idx_sorted), _p(tile_range), _p(tile_order), _p(final_T), _p(ncontrib), _p(out),
+                    _p(radius), _p(idx_sorted), _p(tile_range), _p(final_T), _p(ncontrib), _p(out),
                     host_t.data_ptr(), _p(ws), ws.numel(), ev_arr, stream)
             if same_dev:
                 _lib.check(lib.pxb_render_forward(*args), "pxb_render_forward")
@@ -201,7 +197,6 @@ class _FusedRender(torch.autograd.Function):
             cap = _CAPACITY[ckey] = int(n * 1.25) + 65536
         ctx.save_for_backward(pos, sc, rot, sh, intr_c, extr_c, cc, rec, depth, radius, idx_sorted, tile_range, final_T,
                               ncontrib)
-        ctx.tile_order = tile_order
         ctx.meta = (int(sh_degree), W, H, float(bg), int(with_depth), n_extra, S, Cc,
                     intr.shape, extr.shape, cam_center.shape, opacity.shape)
         ctx.mark_non_differentiable(radius)
@@ -242,8 +237,7 @@ class _FusedRender(torch.autograd.Function):
             evs, ev_arr = _stage_events(timer, _BWD_STAGES)
             _lib.check(lib.pxb_render_backward(
                 P, sh_degree, _p(pos), _p(sc), _p(rot), _p(sh), n_extra, with_depth, _p(intr), _p(extr), _p(cc), W, H, bg,
-                S, _p(rec), _p(depth), _p(radius), _p(idx_sorted), _p(tile_range), _p(ctx.tile_order), _p(final_T),
-                _p(ncontrib), _p(g),
+                S, _p(rec), _p(depth), _p(radius), _p(idx_sorted), _p(tile_range), _p(final_T), _p(ncontrib), _p(g),
                 _p(grec), _p(d_pos), _p(d_sc), _p(d_rot), _p(d_op), _p(None if d_rgb is not None else d_sh), _p(d_rgb),
                 _p(d_extra), _p(d_ndc), _p(d_cam), ev_arr, _raw_stream(dev.index)), "pxb_render_backward")
         _lib.count_launches("pxb_render_backward", W, H)

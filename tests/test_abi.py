@@ -102,7 +102,7 @@ def test_argument_errors_are_return_codes():
     assert L.pxb_p2p_allreduce(arr, 6, 0, 0, 2, null) == -4                                            # n_f32 % (4*world)
     assert L.pxb_nvls_allreduce(null, 8, 0, 0, 2, null) == -1
     assert L.pxb_render_forward(0, 3, *([null] * 6), 0, 0, null, null, null, 8, 8, 0.2, 1.3, 1.0, 12, 100,
-                                *([null] * 11), 0, null, null) == -1                                   # P = 0
+                                *([null] * 10), 0, null, null) == -1                                   # P = 0
     assert L.pxb_fused_backward(10, 5, *([one] * 4), 0, 0, one, one, one, 8, 8, 12, *([one] * 13), null) == -2  # SH degree
     assert L.pxb_fused_backward(10, 3, *([one] * 4), 0, 0, one, one, one, 8, 8, 12, one, one, one, one, one, one, one,
                                 null, null, one, one, one, null) == -1                                 # neither d_shs nor d_rgb
