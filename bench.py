@@ -125,11 +125,18 @@ class ClockSampler:
             N, h, reasons = self._handle()
             self.nvml = N
 
+            mode = os.environ.get("PXB_BENCH_SAMPLER", "1")
+
             def loop():
                 while not self._stop.is_set():
                     try:
-                        self.samples.append((time.perf_counter(), float(N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM)),
-                                             int(reasons(h))))
+                        t0 = time.perf_counter()
+                        clk = float(N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM))
+                        t1 = time.perf_counter()
+                        rs = int(reasons(h)) if mode != "2" else 0
+                        t2 = time.perf_counter()
+                        self.samples.append((t0, clk, rs))
+                        self.query_ms = max(getattr(self, "query_ms", (0.0, 0.0)), (1e3 * (t1 - t0), 1e3 * (t2 - t1)))
                     except Exception:
                         pass
                     self._stop.wait(self.interval)
@@ -504,19 +511,21 @@ def _main(out_f):
     # ---- device-resident timed region --------------------------------------------------
     sampler = ClockSampler(local)
     DEBUG_MARKS = os.environ.get("PXB_BENCH_STEP_MARKS") == "1"   # developer knobs (timeline of the timed pass)
-    if rank == 0 and os.environ.get("PXB_BENCH_SAMPLER", "1") == "1":
+    if rank == 0 and os.environ.get("PXB_BENCH_SAMPLER", "1") != "0":
         sampler.start()  # before the warm-up: the sampler's own start-up must not overlap the timed region
     # Untimed settling phase before the W warm-up steps: the process has spent seconds on the host building the
     # scene, the GPU has idled meanwhile, and on a fresh box the first few hundred milliseconds of steps also
-    # page code in.  Measured: with only W = 5 warm-up steps (10 ms of GPU work) the timed region that followed
-    # occasionally contained a 10-160 ms stall that the second pass over the same steps never showed.  So the
-    # step runs continuously for PREWARM_S seconds of wall clock first (every rank the same number of steps).
+    # page code in.  So the step runs continuously for PREWARM_S seconds of wall clock first (every rank the same
+    # number of steps), with exactly the allocation pattern of the timed loop.
     PREWARM_S = float(os.environ.get("PXB_BENCH_PREWARM_S", "0.6"))
     n_pre = 0
     t_pre = time.perf_counter()
     while PREWARM_S > 0:
         for _ in range(16):
-            step_fn(n_pre)
+            # same object lifetimes as the timed loop below (the previous step's outputs stay referenced while the
+            # next step runs): the caching allocator must reach THAT steady state here.  Discarding the result
+            # instead let the first timed steps call cudaMalloc (measured: one 10-250 ms stall in timed step 2)
+            loss, out = step_fn(n_pre)
             n_pre += 1
         stop = torch.tensor([1.0 if time.perf_counter() - t_pre >= PREWARM_S else 0.0], device=dev)
         if world > 1:
@@ -524,7 +533,7 @@ def _main(out_f):
         if stop.item() > 0:
             break
     for s in range(W_):
-        step_fn(s)
+        loss, out = step_fn(s)
     sync()
     if rank == 0:
         sampler.wait_first(3.0)
@@ -551,6 +560,7 @@ def _main(out_f):
     if DEBUG_MARKS and rank == 0:
         print("timed pass: device ms since start per step:", [round(e0.elapsed_time(m), 3) for m in marks], file=sys.stderr)
         print("timed pass: host ms between step returns:", [round(1e3 * (b - a), 3) for a, b in zip(host_t, host_t[1:])], file=sys.stderr)
+        print("sampler: slowest (clock, reasons) query ms:", getattr(sampler, "query_ms", None), file=sys.stderr)
     if rank == 0:
         sampler.mark_end()
     ms = e0.elapsed_time(e1)

@@ -631,12 +631,12 @@ static int launch_fwd(const float* rec, const int* idx_sorted, const int* tile_r
     return launch_fwd_v<CH, S, false>(rec, idx_sorted, tile_range, bg, C, W, H, final_T, ncontrib, out, s);
 }
 
-// C <= 4: 3 CTAs per SM with 80 registers (no spills, no re-materialised addresses in the pair loop) or 4 CTAs
-// with 64 (PXB_BWD_OCC=4); measured on cfg4, see DESIGN.md section 4
+// C <= 4: 4 CTAs per SM with 64 registers (24 bytes spilled) -- measured on cfg4 0.557 ms, against 0.617 ms for
+// 3 CTAs with 80 registers and no spill (PXB_BWD_OCC=3): the pair loop is issue bound and wants the warps
 static int bwd_occupancy() {
     static const int v = [] {
         const char* e = getenv("PXB_BWD_OCC");
-        return (e && e[0] == '4') ? 4 : 3;
+        return (e && e[0] == '3') ? 3 : 4;
     }();
     return v;
 }

@@ -944,15 +944,12 @@ int pxb_fused_backward(int P, int sh_degree, const float* pos, const float* scal
     cudaStream_t s = (cudaStream_t)stream;
     const int nb = blocks_for(P, kFThreads);
     const size_t smem = (size_t)kFThreads * kShPitch * sizeof(float);
-    // 121 registers un-capped (4 CTAs of 128 threads per SM); PXB_FBWD_OCC=5 caps at 96 (5 CTAs, 52 bytes spilled)
-    static const int occ = [] { const char* e = getenv("PXB_FBWD_OCC"); return (e && e[0] == '5') ? 5 : 4; }();
-#define PXB_LAUNCH_BWD_V(KA, MINB)                                                                                      \
-    PXB_CUDA_OK(launch_k(fused_bwd_kernel<KA, MINB>, dim3(nb), dim3(kFThreads), smem, s, P, pos, scales,                  \
+    // 121 registers (4 CTAs of 128 threads per SM).  Capping at 96 for a fifth CTA was measured: 0.130 vs 0.133 ms,
+    // not worth the 52 spilled bytes
+#define PXB_LAUNCH_BWD(KA)                                                                                              \
+    PXB_CUDA_OK(launch_k(fused_bwd_kernel<KA, 4>, dim3(nb), dim3(kFThreads), smem, s, P, pos, scales,                     \
                          (const float4*)quats, shs, n_extra, with_depth, intr, extr, cam_center, W, H, S, depth, radius,  \
                          grec, d_pos, d_scales, (float4*)d_quats, d_opacity, d_shs, d_rgb, d_extra, d_ndc, d_cam))
-#define PXB_LAUNCH_BWD(KA)                    \
-    if (occ == 5) { PXB_LAUNCH_BWD_V(KA, 5); } \
-    else { PXB_LAUNCH_BWD_V(KA, 4); }
     switch (sh_degree) {
         case 0: PXB_LAUNCH_BWD(1); break;
         case 1: PXB_LAUNCH_BWD(4); break;
@@ -960,7 +957,6 @@ int pxb_fused_backward(int P, int sh_degree, const float* pos, const float* scal
         default: PXB_LAUNCH_BWD(16); break;
     }
 #undef PXB_LAUNCH_BWD
-#undef PXB_LAUNCH_BWD_V
     return (int)cudaGetLastError();
 }
 
