@@ -21,6 +21,13 @@ Two sources, both the reference itself:
       `lpips` import, an absent third-party package the L1/SSIM code never touches, is stubbed),
       runs l1_loss / l2_loss / psnr / ssim and the get_loss_dict combination with autograd on small
       seeded images and stores inputs, values and gradients in tests/golden/ref_loss.npz.
+
+  python oracle/make_golden.py --from-ref-plugin
+      (this container, CPU) executes the reference's OWN plugin file pointrix/model/renderer/msplat.py where
+      it lies, against a stub `BaseObject`, the reference's real registry.py / renderer_utils.py and a module
+      `msplat` backed by the CPU oracle's six operators: render_iter (rgb / rgb+depth, SH degree 3 / 1,
+      autograd gradients), render_batch and update_sh_degree -> tests/golden/ref_plugin.npz.  Pins the
+      plugin glue (SH degree mask, +0.5 clamp, nearest = 0.2, depth channel, ndc.grad, batch reductions).
 """
 from __future__ import annotations
 
@@ -200,8 +207,120 @@ def from_ref_loss(out_path):
     print("wrote", out_path, {k: tuple(v.shape) for k, v in G.items() if k.endswith("_pred")})
 
 
+def load_reference_plugin():
+    """The reference's OWN plugin file, pointrix/model/renderer/msplat.py, executed where it lies against stubs
+    of what it imports: `BaseObject` (pointrix/utils/base.py:24-39 needs omegaconf -- a 15-line
+    stand-in that parses the dataclass Config and calls setup), the REAL pointrix/utils/registry.py and
+    pointrix/model/renderer/utils/renderer_utils.py loaded from the reference tree, and a module `msplat`
+    whose six operators are the CPU oracle (oracle/msplat_oracle.py).  Returns the module: its MsplatRender
+    class is the reference's code, line for line, driving our restatement of the operators."""
+    import importlib.util
+    import types
+    from dataclasses import fields
+
+    import torch
+
+    from oracle import msplat_oracle as O
+
+    ref = "/root/reference/pointrix"
+
+    def pkg(name):
+        m = types.ModuleType(name)
+        m.__path__ = []
+        sys.modules[name] = m
+        return m
+
+    def load(name, path):
+        spec = importlib.util.spec_from_file_location(name, path)
+        m = importlib.util.module_from_spec(spec)
+        sys.modules[name] = m
+        spec.loader.exec_module(m)
+        return m
+
+    for name in ("pointrix", "pointrix.utils", "pointrix.model", "pointrix.model.renderer", "pointrix.model.renderer.utils"):
+        pkg(name)
+
+    class BaseObject:  # pointrix/utils/base.py:24-39 without omegaconf
+        def __init__(self, cfg=None, *args, **kwargs):
+            known = {f.name for f in fields(self.Config)}
+            self.cfg = self.Config(**{k: v for k, v in (cfg or {}).items() if k in known})
+            self.setup(*args, **kwargs)
+
+        def setup(self, *args, **kwargs):
+            pass
+
+    base = types.ModuleType("pointrix.utils.base")
+    base.BaseObject = BaseObject
+    sys.modules["pointrix.utils.base"] = base
+    load("pointrix.utils.registry", os.path.join(ref, "utils", "registry.py"))
+    load("pointrix.model.renderer.utils.renderer_utils", os.path.join(ref, "model", "renderer", "utils", "renderer_utils.py"))
+    ms = types.ModuleType("msplat")
+    for fn in ("compute_sh", "project_point", "compute_cov3d", "ewa_project", "sort_gaussian", "alpha_blending"):
+        setattr(ms, fn, getattr(O, fn))
+    sys.modules["msplat"] = ms
+    # the reference moves `position` to the GPU by hand (msplat.py:94-95); this container has none
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    return load("pointrix.model.renderer.msplat", os.path.join(ref, "model", "renderer", "msplat.py"))
+
+
+def from_ref_plugin(out_path):
+    """Golden vectors of the plugin level: MsplatRender.render_iter / render_batch of the reference's own
+    msplat.py (see load_reference_plugin) on a small seeded scene, with autograd gradients."""
+    import numpy as np
+    import torch
+
+    from bench import load_scene_module
+
+    scene = load_scene_module()
+    mod = load_reference_plugin()
+    P, W, H = 1500, 96, 64
+    _, sc, _ = scene.make_config("cfg1", P=P, views=1)
+    cams = scene.make_cameras(2, W, H, seed=1)
+    g = torch.Generator().manual_seed(2)
+    out = {"P": np.int64(P), "W": np.int64(W), "H": np.int64(H)}
+    for k, v in sc.items():
+        out[k] = v.numpy()
+    for k, v in cams.items():
+        out["cam_" + k] = v.numpy()
+    for tag, deg, depth_ch in (("a", 3, False), ("b", 1, True)):
+        r = mod.MsplatRender({"render_depth": depth_ch}, True, "cpu")
+        r.sh_degree = deg
+        leaves = {k: v.clone().requires_grad_() for k, v in sc.items()}
+        o = r.render_iter(H, W, cams["extrinsic_matrix"][0], cams["intrinsic_params"], cams["camera_center"][0], **leaves)
+        img = torch.cat(list(o["rendered_features_split"].values()), 0)
+        dimg = torch.randn(img.shape, generator=g)
+        img.backward(dimg)
+        out[f"{tag}_img"], out[f"{tag}_dimg"] = img.detach().numpy(), dimg.numpy()
+        out[f"{tag}_radii"] = o["radii"].numpy()
+        out[f"{tag}_visibility"] = o["visibility"].numpy()
+        out[f"{tag}_g_ndc"] = o["uv_points"].grad.numpy()
+        for k, v in leaves.items():
+            out[f"{tag}_g_{k}"] = v.grad.numpy()
+    # render_batch: two views, reductions of msplat.py:160-213
+    r = mod.MsplatRender({}, True, "cpu")
+    r.sh_degree = 3
+    with torch.no_grad():
+        rb = r.render_batch(dict(height=H, width=W, extrinsic_matrix=cams["extrinsic_matrix"],
+                                 intrinsic_params=cams["intrinsic_params"], camera_center=cams["camera_center"], **sc))
+    out["batch_rgb"] = rb["rgb"].numpy()
+    out["batch_radii"] = rb["radii"].numpy()
+    out["batch_visibility"] = rb["visibility"].numpy()
+    # update_sh_degree / state_dict (msplat.py:215-248)
+    r2 = mod.MsplatRender({"update_sh_iter": 10, "max_sh_degree": 2}, False, "cpu")
+    degs = []
+    for step in range(0, 45):
+        r2.update_sh_degree(step)
+        degs.append(r2.sh_degree)
+    out["sh_schedule"] = np.array(degs, dtype=np.int64)
+    out["bg_black"] = np.float64(r2.bg_color)
+    np.savez_compressed(out_path, **out)
+    print("wrote", out_path, {k: getattr(v, "shape", v) for k, v in out.items() if k.startswith(("a_", "batch"))})
+
+
 if __name__ == "__main__":
-    if "--from-ref-loss" in sys.argv:
+    if "--from-ref-plugin" in sys.argv:
+        from_ref_plugin(os.path.join(ROOT, "tests", "golden", "ref_plugin.npz"))
+    elif "--from-ref-loss" in sys.argv:
         from_ref_loss(os.path.join(ROOT, "tests", "golden", "ref_loss.npz"))
     elif "--from-ref-tests" in sys.argv:
         from_ref_tests(os.path.join(ROOT, "tests", "golden", "ref_test_oracles.npz"))

@@ -10,7 +10,7 @@ import math
 import pytest
 import torch
 
-from tests.util import rel_err, scene_inputs
+from tests.util import elem_bad_fraction, rel_err, scene_inputs
 
 pytestmark = pytest.mark.gpu
 
@@ -34,9 +34,11 @@ def _cam(cams, i=0):
 # ---------------------------------------------------------------------------
 # per-operator parity against the compiled reference
 # ---------------------------------------------------------------------------
-@pytest.mark.parametrize("P,W,H", [(10_000, 800, 800), (300_000, 1297, 840), (1_000_000, 1920, 1080)])
+@pytest.mark.parametrize("P,W,H", [(10_000, 800, 800), (300_000, 1297, 840), (1_000_000, 1920, 1080),
+                                   (3_000_000, 1297, 840), (1_000_000, 979, 546)])  # ... cfg3 and cfg5 at full size
 def test_per_gaussian_chain_bit_exact(pb, ref, P, W, H):
-    c, sc, cams = scene_inputs("cfg4" if P >= 1_000_000 else "cfg2", P=P, W=W, H=H)
+    cfg = "cfg3" if P >= 3_000_000 else ("cfg4" if P >= 1_000_000 else "cfg2")
+    c, sc, cams = scene_inputs(cfg, P=P, W=W, H=H)
     E, intr, cc = _cam(cams)
     extr = E[:3, :].contiguous()
     C_ = ref.C()
@@ -59,9 +61,9 @@ def test_per_gaussian_chain_bit_exact(pb, ref, P, W, H):
         assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
 
 
-@pytest.mark.parametrize("P,W,H", [(10_000, 800, 800), (1_000_000, 1920, 1080)])
+@pytest.mark.parametrize("P,W,H", [(10_000, 800, 800), (1_000_000, 1920, 1080), (3_000_000, 1297, 840)])
 def test_sort_gaussian_bit_exact(pb, ref, P, W, H):
-    c, sc, cams = scene_inputs("cfg4" if P >= 1_000_000 else "cfg1", P=P, W=W, H=H)
+    c, sc, cams = scene_inputs("cfg3" if P >= 3_000_000 else ("cfg4" if P >= 1_000_000 else "cfg1"), P=P, W=W, H=H)
     E, intr, cc = _cam(cams)
     f = ref.render_forward(H, W, E, intr, cc, **sc)
     ids, tr, keys = pb.sort_gaussian(f["uv"], f["depth"], W, H, f["radius"], f["tiles"], return_keys=True)
@@ -210,9 +212,12 @@ def _renderer(pb, render_depth=False, sh_degree=3, white_bg=True):
 
 
 @pytest.mark.parametrize("P,W,H,deg,depth_ch", [(10_000, 800, 800, 3, False), (10_000, 800, 800, 1, True),
-                                                (200_000, 979, 546, 3, True), (1_000_000, 1920, 1080, 3, False)])
+                                                (200_000, 979, 546, 3, True), (1_000_000, 1920, 1080, 3, False),
+                                                (1_000_000, 979, 546, 3, False),     # cfg5 at full size (camera grads)
+                                                (3_000_000, 1297, 840, 3, False)])   # cfg3 at full size
 def test_render_iter_vs_ref(pb, ref, P, W, H, deg, depth_ch):
-    c, sc, cams = scene_inputs("cfg4" if P >= 500_000 else "cfg1", P=P, W=W, H=H)
+    cfg = "cfg3" if P >= 3_000_000 else ("cfg4" if P >= 500_000 else "cfg1")
+    c, sc, cams = scene_inputs(cfg, P=P, W=W, H=H)
     E, intr, cc = _cam(cams)
     f = ref.render_forward(H, W, E, intr, cc, **sc, sh_degree=deg, render_depth=depth_ch)
     r = _renderer(pb, depth_ch, deg)
@@ -235,6 +240,19 @@ def test_render_iter_vs_ref(pb, ref, P, W, H, deg, depth_ch):
     assert rel_err(E_l.grad[:3], b["extr"]) <= GRAD_TOL
     assert E_l.grad[3].abs().max().item() == 0
     assert rel_err(cc_l.grad, b["camera_center"]) <= 5 * GRAD_TOL
+    # per-element reading of the same tolerance (tests/util.py): the fraction of gradient entries off by more
+    # than 1e-3 relative (+ 1e-3 of the typical magnitude).  The reference's own atomics make two of ITS runs
+    # differ, so the bar is that noise floor: a second reference backward is the yardstick.
+    b2 = ref.render_backward(f, dimg, sc["position"], sc["opacity"], sc["scaling"], sc["rotation"], sc["shs"], cc,
+                             sh_degree=deg, render_depth=depth_ch, camera_grads=True)
+    report = {}
+    for k in ("position", "scaling", "rotation", "opacity", "shs"):
+        ours, noise = elem_bad_fraction(leaves[k].grad, b[k]), elem_bad_fraction(b2[k], b[k])
+        report[k] = (ours, noise)
+        assert ours <= max(2e-3, 3.0 * noise), (k, ours, noise)
+    ours, noise = elem_bad_fraction(out["uv_points"].grad, b["ndc"]), elem_bad_fraction(b2["ndc"], b["ndc"])
+    assert ours <= max(2e-3, 3.0 * noise), ("ndc", ours, noise)
+    print(f"per-element bad fraction (ours, reference run-to-run) P={P}: {report}")
 
 
 def test_render_iter_extra_features_and_fallback(pb, ref):
@@ -260,6 +278,112 @@ def test_render_iter_extra_features_and_fallback(pb, ref):
                                        sc["rotation"], sc["shs"], torch.cat([normals, flow], -1), ndc)
     assert torch.equal(radius, out["radii"])
     assert (feats - img).abs().max().item() <= 1e-5 * max(1.0, img.abs().max().item())
+
+
+def test_fused_path_image_is_bit_identical_to_the_operator_path_at_full_size(pb):
+    """render_iter bins with tighter tile lists than the operator API (which keeps the reference's lists bit for
+    bit): no (pixel, Gaussian) pair that blends is dropped and the blend arithmetic is the same, so at cfg4's
+    full size the two images must be EQUAL, not close -- and so must ncontrib-driven outputs (final alpha)."""
+    P, W, H = 1_000_000, 1920, 1080
+    c, sc, cams = scene_inputs("cfg4", P=P, W=W, H=H)
+    E, intr, cc = _cam(cams)
+    r = _renderer(pb, True, 3)
+    with torch.no_grad():
+        out = r.render_iter(H, W, E, intr, cc, **sc)
+        img = torch.cat(list(out["rendered_features_split"].values()), 0)
+        ndc = torch.zeros(P, 2, device="cuda")
+        feats, radius = r._render_iter_ops(H, W, E[:3, :], intr, cc, sc["position"], sc["opacity"], sc["scaling"],
+                                           sc["rotation"], sc["shs"], None, ndc)
+    assert torch.equal(radius, out["radii"])
+    assert torch.equal(feats, img), f"max abs diff {(feats - img).abs().max().item():.3e}"
+
+
+def test_rasterization_vs_ref(pb, ref):
+    """a13: msplat.rasterization (msplat/msplat/__init__.py:22-93): project (default nearest = 0.0) -> cov3d ->
+    ewa -> sort -> blend on user features, forward and backward, against the same sequence of the compiled
+    reference's entry points."""
+    P, W, H = 50_000, 640, 480
+    c, sc, cams = scene_inputs("cfg2", P=P, W=W, H=H)
+    E, intr, cc = _cam(cams)
+    extr = E[:3, :].contiguous()
+    g = torch.Generator().manual_seed(11)
+    feature = torch.rand(P, 5, generator=g).cuda()
+    C_ = ref.C()
+    # the reference sequence (its Python wrappers restated over the raw _C entry points)
+    uv_r, depth_r = C_.project_point_forward(sc["position"], intr, extr, W, H, 0.0, 1.3)
+    vis_r = (depth_r != 0).reshape(-1)
+    cov_r = C_.compute_cov3d_forward(sc["scaling"], sc["rotation"], vis_r)
+    conic_r, radius_r, tiles_r = C_.ewa_project_forward(sc["position"], cov_r, intr, extr, uv_r, W, H, vis_r)
+    idx_r, tr_r = ref.sort_gaussian(uv_r, depth_r, W, H, radius_r, tiles_r)
+    img_r, fT_r, nc_r = C_.alpha_blending_forward(uv_r, conic_r, sc["opacity"], feature, idx_r, tr_r, 0.5, W, H)
+    leaves = {k: sc[k].clone().requires_grad_() for k in ("position", "scaling", "rotation", "opacity")}
+    feat_l = feature.clone().requires_grad_()
+    ndc = torch.zeros(P, 2, device="cuda", requires_grad=True)
+    img = pb.rasterization(leaves["position"], leaves["scaling"], leaves["rotation"], leaves["opacity"], feat_l, intr, extr,
+                           W, H, 0.5, ndc)
+    assert img.shape == (5, H, W)
+    assert (img - img_r).abs().max().item() <= IMG_TOL
+    dimg = torch.randn(img.shape, generator=g).cuda()
+    img.backward(dimg)
+    d_uv, d_conic, d_op, d_feat = C_.alpha_blending_backward(uv_r, conic_r, sc["opacity"], feature, idx_r, tr_r, 0.5, W, H,
+                                                             fT_r, nc_r, dimg.contiguous())
+    d_xyz_e, d_cov, _, _ = C_.ewa_project_backward(sc["position"], cov_r, intr, extr, radius_r, d_conic)
+    d_scale, d_quat = C_.compute_cov3d_backward(sc["scaling"], sc["rotation"], vis_r, d_cov)
+    d_xyz_p, _, _ = C_.project_point_backward(sc["position"], intr, extr, W, H, uv_r, depth_r, d_uv, torch.zeros_like(depth_r))
+    assert rel_err(feat_l.grad, d_feat) <= GRAD_TOL
+    assert rel_err(leaves["opacity"].grad, d_op) <= GRAD_TOL
+    assert rel_err(leaves["position"].grad, d_xyz_e + d_xyz_p) <= GRAD_TOL
+    assert rel_err(leaves["scaling"].grad, d_scale) <= GRAD_TOL
+    assert rel_err(leaves["rotation"].grad, d_quat) <= GRAD_TOL
+    assert rel_err(ndc.grad, d_uv * torch.tensor([0.5 * W, 0.5 * H], device="cuda")) <= GRAD_TOL
+    # Gaussians behind the camera (possible only with nearest = 0): the reference's key kernel sign-extends the
+    # negative depth bits into the tile id (undefined behaviour, DESIGN.md section 8); here they are binned as
+    # unsigned words and the call must neither crash nor touch the pixels in front
+    pos_b = sc["position"].clone()
+    pos_b[: P // 2] = cc + 2.0 * (cc / cc.norm())  # half the cloud moved behind the camera
+    img_b = pb.rasterization(pos_b, sc["scaling"], sc["rotation"], sc["opacity"], feature, intr, extr, W, H, 0.5)
+    torch.cuda.synchronize()
+    assert torch.isfinite(img_b).all()
+
+
+def test_render_iter_vs_reference_plugin_golden(pb):
+    """The CUDA plugin against tests/golden/ref_plugin.npz: outputs of the reference's OWN plugin file
+    (pointrix/model/renderer/msplat.py executed where it lies, oracle/make_golden.py --from-ref-plugin) driving
+    the CPU oracle's operators.  Exact CPU arithmetic vs the GPU's MUFU approximations: radii may flip at ceil
+    boundaries for a handful of Gaussians, and isolated pixels at alpha / termination thresholds."""
+    import os
+
+    import numpy as np
+
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_plugin.npz"))
+    t = lambda k: torch.from_numpy(z[k]).cuda()  # noqa: E731
+    H, W, P = int(z["H"]), int(z["W"]), int(z["P"])
+    E, intr, cc = t("cam_extrinsic_matrix"), t("cam_intrinsic_params"), t("cam_camera_center")
+    names = ("position", "opacity", "scaling", "rotation", "shs")
+    for tag, deg, depth_ch in (("a", 3, False), ("b", 1, True)):
+        r = _renderer(pb, depth_ch, deg)
+        leaves = {k: t(k).clone().requires_grad_() for k in names}
+        o = r.render_iter(H, W, E[0], intr, cc[0], **leaves)
+        img = torch.cat(list(o["rendered_features_split"].values()), 0)
+        mism = int((o["radii"] != t(f"{tag}_radii")).sum())
+        assert mism <= max(2, P // 500), mism
+        err = (img - t(f"{tag}_img")).abs() / max(1.0, float(t(f"{tag}_img").abs().max()))
+        assert float((err > 2e-4).float().mean()) <= 2e-3 and float(err.max()) <= 5e-2
+        if mism == 0:
+            img.backward(t(f"{tag}_dimg"))
+            for k in names:
+                gr = t(f"{tag}_g_{k}").double()
+                rel = float((leaves[k].grad.double() - gr).norm() / gr.norm().clamp_min(1e-30))
+                assert rel <= 1e-2, (tag, k, rel)
+    r = _renderer(pb, False, 3)
+    with torch.no_grad():
+        rb = r.render_batch(dict(height=H, width=W, extrinsic_matrix=E, intrinsic_params=intr, camera_center=cc,
+                                 **{k: t(k) for k in names}))
+    assert rb["rgb"].shape == tuple(z["batch_rgb"].shape)
+    assert int((rb["radii"] != t("batch_radii")).sum()) <= max(2, P // 500)
+    assert int((rb["visibility"] != t("batch_visibility")).sum()) <= max(2, P // 500)
+    err = (rb["rgb"] - t("batch_rgb")).abs()
+    assert float((err > 2e-4).float().mean()) <= 2e-3
 
 
 def test_render_batch_reductions(pb, ref):

@@ -245,3 +245,18 @@ def test_factored_exchange_protocol_gloo_world2():
         assert p.exitcode == 0
     for rank, err, same_bits, mag in res:
         assert mag > 0 and err <= 1e-5 and same_bits, (rank, err, same_bits)
+
+
+def test_plugin_host_logic_matches_reference_plugin_golden():
+    """update_sh_degree schedule and background colour of the reference's own MsplatRender
+    (tests/golden/ref_plugin.npz, oracle/make_golden.py --from-ref-plugin) -- host logic, no GPU."""
+    import numpy as np
+
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_plugin.npz"))
+    r = pb.MsplatRender({"update_sh_iter": 10, "max_sh_degree": 2}, False, "cpu")
+    degs = []
+    for step in range(0, 45):
+        r.update_sh_degree(step)
+        degs.append(r.sh_degree)
+    assert degs == z["sh_schedule"].tolist()
+    assert r.bg_color == float(z["bg_black"])

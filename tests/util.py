@@ -26,3 +26,15 @@ def scene_inputs(name="cfg1", P=None, views=1, device="cuda", W=None, H=None):
         c["W"], c["H"] = W, H
         cams = scene.make_cameras(views, W, H, seed=1)
     return c, to_dev(sc, device), to_dev(cams, device)
+
+
+def elem_bad_fraction(a: torch.Tensor, b: torch.Tensor, rtol: float = 1e-3) -> float:
+    """Per-element reading of 'relative 1e-3 on gradients': the fraction of elements with
+    |a - b| > rtol * |b| + rtol * typical(|b|), typical = the median magnitude of the non-zero reference
+    entries (the absolute floor every fp32 sum of signed terms needs; the max-normalised rel_err above
+    uses the LARGEST entry as that floor and so barely looks at small gradients)."""
+    a, b = a.double().cpu().reshape(-1), b.double().cpu().reshape(-1)
+    nz = b.abs()[b != 0]
+    floor = nz.median().item() if nz.numel() else 0.0
+    bad = (a - b).abs() > rtol * b.abs() + rtol * floor
+    return bad.double().mean().item()
