@@ -280,22 +280,44 @@ def test_render_iter_extra_features_and_fallback(pb, ref):
     assert (feats - img).abs().max().item() <= 1e-5 * max(1.0, img.abs().max().item())
 
 
-def test_fused_path_image_is_bit_identical_to_the_operator_path_at_full_size(pb):
-    """render_iter bins with tighter tile lists than the operator API (which keeps the reference's lists bit for
-    bit): no (pixel, Gaussian) pair that blends is dropped and the blend arithmetic is the same, so at cfg4's
-    full size the two images must be EQUAL, not close -- and so must ncontrib-driven outputs (final alpha)."""
+def test_tight_tile_lists_render_the_same_bits_at_full_size(pb):
+    """render_iter bins with tighter tile lists than the reference (only the tiles the alpha >= 1/255 ellipse can
+    reach).  No (pixel, Gaussian) pair that blends may be dropped, and the per-pixel order is unchanged, so
+    blending the SAME records through both sets of lists must give EQUAL images and transmittances -- not
+    close ones -- at cfg4's full size.  (Against the operator path the image differs by one ulp of the SH
+    colour, 2.4e-7: that path evaluates SH with torch's normalise instead of the fused kernel's.)"""
+    import ctypes as C
+
+    from pointrix_b200 import _lib, ops
+
     P, W, H = 1_000_000, 1920, 1080
     c, sc, cams = scene_inputs("cfg4", P=P, W=W, H=H)
     E, intr, cc = _cam(cams)
-    r = _renderer(pb, True, 3)
-    with torch.no_grad():
-        out = r.render_iter(H, W, E, intr, cc, **sc)
-        img = torch.cat(list(out["rendered_features_split"].values()), 0)
-        ndc = torch.zeros(P, 2, device="cuda")
-        feats, radius = r._render_iter_ops(H, W, E[:3, :], intr, cc, sc["position"], sc["opacity"], sc["scaling"],
-                                           sc["rotation"], sc["shs"], None, ndc)
-    assert torch.equal(radius, out["radii"])
-    assert torch.equal(feats, img), f"max abs diff {(feats - img).abs().max().item():.3e}"
+    extr = E[:3, :].contiguous()
+    S = _lib.lib.pxb_record_stride(3)
+    dev = sc["position"].device
+    stream = ops._stream(dev)
+    res = {}
+    for tight in (0, 1):
+        rec = torch.empty(P, S, device=dev)
+        depth = torch.empty(P, device=dev)
+        radius = torch.empty(P, dtype=torch.int32, device=dev)
+        tiles = torch.empty(P, dtype=torch.int32, device=dev)
+        _lib.launch("pxb_fused_forward", P, 3, ops._p(sc["position"]), ops._p(sc["scaling"]), ops._p(sc["rotation"]),
+                    ops._p(sc["opacity"]), ops._p(sc["shs"]), ops._p(None), 0, 0, ops._p(intr), ops._p(extr), ops._p(cc), W, H,
+                    0.2, 1.3, S, tight, ops._p(rec), ops._p(depth), ops._p(radius), ops._p(tiles), stream)
+        ids, tr = ops._bin(rec, S, depth, radius, tiles, W, H, tight=bool(tight))
+        out = torch.empty(3, H, W, device=dev)
+        fT = torch.empty(H, W, device=dev)
+        nc = torch.empty(H, W, dtype=torch.int32, device=dev)
+        _lib.launch("pxb_blend_forward", ops._p(rec), S, 3, ops._p(ids), ops._p(tr), 1.0, W, H, ops._p(fT), ops._p(nc),
+                    ops._p(out), stream)
+        res[tight] = (rec, radius, ids.numel(), out, fT, nc)
+    assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][1], res[1][1])   # same records, same radii
+    assert res[1][2] < 0.8 * res[0][2]                                               # ... far fewer intersections
+    assert torch.equal(res[0][3], res[1][3]), f"max abs diff {(res[0][3] - res[1][3]).abs().max().item():.3e}"
+    assert torch.equal(res[0][4], res[1][4])
+    assert torch.equal(res[0][5] > 0, res[1][5] > 0)
 
 
 def test_rasterization_vs_ref(pb, ref):
