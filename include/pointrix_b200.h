@@ -210,6 +210,38 @@ int pxb_pixel_loss_forward(int mode, int B, long long n, const float* pred, cons
 int pxb_pixel_loss_backward(int mode, int B, long long n, const float* pred, const float* gt, const float* w,
                             const float* g_map, float* d_pred, void* stream);
 
+/* ---- optimizer step + densification statistics on the Gaussian table: replaces
+ *      torch.optim.Adam.step as driven by BaseOptimizer.update_model (pointrix/optimizer/optimizer.py:128-140;
+ *      six parameter groups, eps 1e-15, examples/gaussian_splatting/configs/nerf.yaml:49-69) and the boolean-mask
+ *      updates of DensificationController.preprocess (pointrix/controller/gs.py:259-333) -- ONE launch.
+ *      A group is a column block of `width` floats per row: columns [param_offset, param_offset + width) of the
+ *      [rows, param_stride] tensors param / exp_avg / exp_avg_sq and columns [grad_offset, ..) of a
+ *      [rows, grad_stride] gradient.  Dense tensors: stride = width, offset = 0.  The reference's features[P,1,3]
+ *      / features_rest[P,15,3] groups take their gradients from columns 0..2 / 3..47 of the fused backward's
+ *      dL/dshs[P,48] rows (grad_stride 48); a model that keeps ONE shs[P,16,3] leaf trains the same two column
+ *      blocks of it with the two learning rates (param_stride 48 as well).
+ *      step: 1-based Adam step (bias correction).  `groups` is a HOST array.
+ *      Statistics (P > 0): ndc_grad[P,2] = sum over the batch's views of ndc.grad, radii[P] = max over views;
+ *      where radii > 0: grad_accum += || ndc_grad * (sx, sy) ||, acc_steps += 1, max_radii = max(max_radii, radii)
+ *      (sx, sy = W/2, H/2 with normalize_grad, gs.py:280-282).  P = 0: Adam only; n_groups = 0: statistics only. ---- */
+#define PXB_MAX_ADAM_GROUPS 8
+typedef struct pxb_adam_group {
+    float* param;
+    const float* grad;
+    float* exp_avg;
+    float* exp_avg_sq;
+    long long rows;
+    int width;
+    int param_stride;
+    int param_offset;
+    int grad_stride;
+    int grad_offset;
+    double lr;
+} pxb_adam_group;
+int pxb_adam_densify_step(const pxb_adam_group* groups, int n_groups, double beta1, double beta2, double eps, int step,
+                          int P, const float* ndc_grad, const int* radii, float sx, float sy, float* grad_accum,
+                          float* acc_steps, float* max_radii, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -28,6 +28,12 @@ Two sources, both the reference itself:
       `msplat` backed by the CPU oracle's six operators: render_iter (rgb / rgb+depth, SH degree 3 / 1,
       autograd gradients), render_batch and update_sh_degree -> tests/golden/ref_plugin.npz.  Pins the
       plugin glue (SH degree mask, +0.5 clamp, nearest = 0.2, depth channel, ndc.grad, batch reductions).
+
+  python oracle/make_golden.py --from-ref-controller
+      (this container, CPU) executes the reference's OWN pointrix/controller/gs.py where it lies (its imports
+      of the config / pose / base-object modules stubbed) and calls DensificationController.preprocess --
+      accumulate_viewspace_grad + the masked updates of grad_accum / acc_steps / max_radii -- three iterations
+      on seeded inputs (two views per iteration) -> tests/golden/ref_controller.npz.
 """
 from __future__ import annotations
 
@@ -317,8 +323,76 @@ def from_ref_plugin(out_path):
     print("wrote", out_path, {k: getattr(v, "shape", v) for k, v in out.items() if k.startswith(("a_", "batch"))})
 
 
+def from_ref_controller(out_path):
+    """Golden vectors of DensificationController.preprocess (pointrix/controller/gs.py:259-333)."""
+    import importlib.util
+    import types
+
+    import numpy as np
+    import torch
+
+    ref = "/root/reference/pointrix"
+
+    def mod(name, **attrs):
+        m = types.ModuleType(name)
+        m.__path__ = []
+        for k, v in attrs.items():
+            setattr(m, k, v)
+        sys.modules[name] = m
+        return m
+
+    def load(name, path):
+        spec = importlib.util.spec_from_file_location(name, path)
+        m = importlib.util.module_from_spec(spec)
+        sys.modules[name] = m
+        spec.loader.exec_module(m)
+        return m
+
+    class BaseObject:
+        pass
+
+    for name in ("pointrix", "pointrix.utils", "pointrix.controller", "pointrix.model", "pointrix.model.utils"):
+        mod(name)
+    mod("pointrix.utils.config", C=lambda *a, **k: None)
+    mod("pointrix.utils.base", BaseObject=BaseObject)
+    mod("pointrix.utils.pose", quat_to_rotmat=lambda q: q)
+    mod("pointrix.model.utils.gaussian_utils", sigmoid_inv=lambda x: x)
+    load("pointrix.utils.registry", os.path.join(ref, "utils", "registry.py"))
+    load("pointrix.controller.base", os.path.join(ref, "controller", "base.py"))
+    gs = load("pointrix.controller.gs", os.path.join(ref, "controller", "gs.py"))
+    ctl = object.__new__(gs.DensificationController)
+    P, W, H = 4000, 640, 360
+    ctl.cfg = types.SimpleNamespace(normalize_grad=True)
+    ctl.width, ctl.height, ctl.device = W, H, "cpu"
+    ctl.grad_accum = torch.zeros((P, 1))
+    ctl.acc_steps = torch.zeros((P, 1))
+    ctl.max_radii = torch.zeros((P,))
+    g = torch.Generator().manual_seed(5)
+    out = {"P": np.int64(P), "W": np.int64(W), "H": np.int64(H)}
+    for it in range(3):
+        views = []
+        radii = torch.zeros(P, dtype=torch.int32)
+        for v in range(2):
+            uv = torch.zeros(P, 2, requires_grad=True)
+            r_v = (torch.rand(P, generator=g) < 0.6) * torch.randint(1, 40, (P,), generator=g, dtype=torch.int32)
+            uv.grad = torch.randn(P, 2, generator=g) * 1e-4 * (r_v > 0)[:, None]
+            views.append(uv)
+            radii = torch.maximum(radii, r_v.to(torch.int32))
+        vis = radii > 0
+        out[f"it{it}_uvgrad"] = torch.stack([u.grad for u in views]).numpy()
+        out[f"it{it}_radii"] = radii.numpy()
+        ctl.preprocess(uv_points=views, visibility=vis, radii=radii)
+        out[f"it{it}_grad_accum"] = ctl.grad_accum.clone().numpy()
+        out[f"it{it}_acc_steps"] = ctl.acc_steps.clone().numpy()
+        out[f"it{it}_max_radii"] = ctl.max_radii.clone().numpy()
+    np.savez_compressed(out_path, **out)
+    print("wrote", out_path)
+
+
 if __name__ == "__main__":
-    if "--from-ref-plugin" in sys.argv:
+    if "--from-ref-controller" in sys.argv:
+        from_ref_controller(os.path.join(ROOT, "tests", "golden", "ref_controller.npz"))
+    elif "--from-ref-plugin" in sys.argv:
         from_ref_plugin(os.path.join(ROOT, "tests", "golden", "ref_plugin.npz"))
     elif "--from-ref-loss" in sys.argv:
         from_ref_loss(os.path.join(ROOT, "tests", "golden", "ref_loss.npz"))

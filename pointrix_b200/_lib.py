@@ -17,7 +17,17 @@ p = C.c_void_p
 i32 = C.c_int
 i64 = C.c_longlong
 f32 = C.c_float
+f64 = C.c_double
 sz = C.c_size_t
+
+
+class AdamGroup(C.Structure):
+    """struct pxb_adam_group (include/pointrix_b200.h)"""
+    _fields_ = [("param", C.c_void_p), ("grad", C.c_void_p), ("exp_avg", C.c_void_p), ("exp_avg_sq", C.c_void_p),
+                ("rows", C.c_longlong), ("width", C.c_int), ("param_stride", C.c_int), ("param_offset", C.c_int),
+                ("grad_stride", C.c_int), ("grad_offset", C.c_int),
+                ("lr", C.c_double)]
+
 
 # name -> (restype, argtypes); mirrors include/pointrix_b200.h one to one
 SIGNATURES = {
@@ -56,6 +66,7 @@ SIGNATURES = {
     "pxb_l1_ssim_backward": (i32, [i32, i32, i32, i32, p, p, p, p, p, i32, f32, f32, p, p]),
     "pxb_pixel_loss_forward": (i32, [i32, i32, i64, p, p, p, p, p, sz, p]),
     "pxb_pixel_loss_backward": (i32, [i32, i32, i64, p, p, p, p, p, p]),
+    "pxb_adam_densify_step": (i32, [p, i32, f64, f64, f64, i32, i32, p, p, f32, f32, p, p, p, p]),
 }
 
 if not os.path.exists(LIB_PATH):
@@ -98,7 +109,7 @@ KERNELS_PER_CALL = {
     "pxb_compute_sh_forward": 1, "pxb_compute_sh_backward": 1, "pxb_bin_prepare": 11, "pxb_sort_gaussian": 8,
     "pxb_pack_records": 1, "pxb_unpack_grads": 1, "pxb_blend_forward": 1, "pxb_blend_backward": 1,
     "pxb_fused_forward": 1, "pxb_fused_backward": 1,
-    "pxb_l1_ssim_forward": 2, "pxb_l1_ssim_loss_forward": 2, "pxb_l1_ssim_backward": 1, "pxb_pixel_loss_forward": 2, "pxb_pixel_loss_backward": 1,
+    "pxb_adam_densify_step": 1, "pxb_l1_ssim_forward": 2, "pxb_l1_ssim_loss_forward": 2, "pxb_l1_ssim_backward": 1, "pxb_pixel_loss_forward": 2, "pxb_pixel_loss_backward": 1,
 }
 
 
