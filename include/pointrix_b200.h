@@ -220,7 +220,8 @@ int pxb_pixel_loss_backward(int mode, int B, long long n, const float* pred, con
  *      / features_rest[P,15,3] groups take their gradients from columns 0..2 / 3..47 of the fused backward's
  *      dL/dshs[P,48] rows (grad_stride 48); a model that keeps ONE shs[P,16,3] leaf trains the same two column
  *      blocks of it with the two learning rates (param_stride 48 as well).
- *      step: 1-based Adam step (bias correction).  `groups` is a HOST array.
+ *      step: the group's own 1-based Adam step count (bias correction; torch.optim keeps it per parameter and
+ *      does not advance it for a parameter without a gradient).  `groups` is a HOST array.
  *      Statistics (P > 0): ndc_grad[P,2] = sum over the batch's views of ndc.grad, radii[P] = max over views;
  *      where radii > 0: grad_accum += || ndc_grad * (sx, sy) ||, acc_steps += 1, max_radii = max(max_radii, radii)
  *      (sx, sy = W/2, H/2 with normalize_grad, gs.py:280-282).  P = 0: Adam only; n_groups = 0: statistics only. ---- */
@@ -236,9 +237,10 @@ typedef struct pxb_adam_group {
     int param_offset;
     int grad_stride;
     int grad_offset;
+    int step;
     double lr;
 } pxb_adam_group;
-int pxb_adam_densify_step(const pxb_adam_group* groups, int n_groups, double beta1, double beta2, double eps, int step,
+int pxb_adam_densify_step(const pxb_adam_group* groups, int n_groups, double beta1, double beta2, double eps,
                           int P, const float* ndc_grad, const int* radii, float sx, float sy, float* grad_accum,
                           float* acc_steps, float* max_radii, void* stream);
 

@@ -25,7 +25,7 @@ class AdamGroup(C.Structure):
     """struct pxb_adam_group (include/pointrix_b200.h)"""
     _fields_ = [("param", C.c_void_p), ("grad", C.c_void_p), ("exp_avg", C.c_void_p), ("exp_avg_sq", C.c_void_p),
                 ("rows", C.c_longlong), ("width", C.c_int), ("param_stride", C.c_int), ("param_offset", C.c_int),
-                ("grad_stride", C.c_int), ("grad_offset", C.c_int),
+                ("grad_stride", C.c_int), ("grad_offset", C.c_int), ("step", C.c_int),
                 ("lr", C.c_double)]
 
 
@@ -66,7 +66,7 @@ SIGNATURES = {
     "pxb_l1_ssim_backward": (i32, [i32, i32, i32, i32, p, p, p, p, p, i32, f32, f32, p, p]),
     "pxb_pixel_loss_forward": (i32, [i32, i32, i64, p, p, p, p, p, sz, p]),
     "pxb_pixel_loss_backward": (i32, [i32, i32, i64, p, p, p, p, p, p]),
-    "pxb_adam_densify_step": (i32, [p, i32, f64, f64, f64, i32, i32, p, p, f32, f32, p, p, p, p]),
+    "pxb_adam_densify_step": (i32, [p, i32, f64, f64, f64, i32, p, p, f32, f32, p, p, p, p]),
 }
 
 if not os.path.exists(LIB_PATH):

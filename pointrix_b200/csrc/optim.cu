@@ -31,13 +31,14 @@ struct OptGroup {
     int p_off;
     int g_stride;      // the same for the gradient tensor
     int g_off;
-    float step_size;   // lr / (1 - beta1^t)
-    int cta_begin;     // first CTA of this group
+    float step_size;      // lr / (1 - beta1^t), t = this group's own step count (torch.optim keeps it per parameter)
+    float inv_bc2_sqrt;   // 1 / sqrt(1 - beta2^t)
+    int cta_begin;        // first CTA of this group
 };
 struct OptArgs {
     OptGroup grp[PXB_MAX_ADAM_GROUPS];
     int n_groups;
-    float beta2, omb1, omb2, eps, inv_bc2_sqrt;  // 1 - beta1, 1 - beta2 (rounded from double), 1 / sqrt(1 - beta2^t)
+    float beta2, omb1, omb2, eps;  // omb = 1 - beta, rounded from double
     // densification statistics (P == 0: none)
     int P;
     int stats_cta_begin;
@@ -107,7 +108,7 @@ __global__ void __launch_bounds__(kOptThreads) adam_densify_kernel(const OptArgs
             //   denom = exp_avg_sq.sqrt() / sqrt(1 - beta2^t) + eps;  param.addcdiv_(exp_avg, denom, value = -lr / (1 - beta1^t))
             const float mk = __fmaf_rn(a.omb1, g[k] - m[k], m[k]);
             const float vk = __fmaf_rn(a.omb2 * g[k], g[k], v[k] * a.beta2);
-            const float denom = __fmaf_rn(__fsqrt_rn(vk), a.inv_bc2_sqrt, a.eps);
+            const float denom = __fmaf_rn(__fsqrt_rn(vk), G.inv_bc2_sqrt, a.eps);
             G.m[pe[k]] = mk;
             G.v[pe[k]] = vk;
             G.p[pe[k]] = __fmaf_rn(-G.step_size, __fdiv_rn(mk, denom), p[k]);
@@ -120,9 +121,9 @@ __global__ void __launch_bounds__(kOptThreads) adam_densify_kernel(const OptArgs
 using namespace pxb;
 
 extern "C" int pxb_adam_densify_step(const pxb_adam_group* groups, int n_groups, double beta1, double beta2, double eps,
-                                     int step, int P, const float* ndc_grad, const int* radii, float sx, float sy,
+                                     int P, const float* ndc_grad, const int* radii, float sx, float sy,
                                      float* grad_accum, float* acc_steps, float* max_radii, void* stream) {
-    if (n_groups < 0 || n_groups > PXB_MAX_ADAM_GROUPS || step < 1 || (n_groups > 0 && groups == nullptr)) return PXB_ERR_BAD_ARG;
+    if (n_groups < 0 || n_groups > PXB_MAX_ADAM_GROUPS || (n_groups > 0 && groups == nullptr)) return PXB_ERR_BAD_ARG;
     if (P > 0 && (!ndc_grad || !radii || !grad_accum || !acc_steps || !max_radii)) return PXB_ERR_BAD_ARG;
     if (P > 0 && (((uintptr_t)ndc_grad) & 7)) return PXB_ERR_ALIGN;
     OptArgs a = {};
@@ -131,12 +132,10 @@ extern "C" int pxb_adam_densify_step(const pxb_adam_group* groups, int n_groups,
     a.omb1 = (float)(1.0 - beta1);
     a.omb2 = (float)(1.0 - beta2);
     a.eps = (float)eps;
-    const double bc1 = 1.0 - pow(beta1, (double)step), bc2 = 1.0 - pow(beta2, (double)step);
-    a.inv_bc2_sqrt = (float)(1.0 / sqrt(bc2));
     long long cta = 0;
     for (int k = 0; k < n_groups; k++) {
         const pxb_adam_group& s = groups[k];
-        if (s.rows < 0 || s.width <= 0 || s.grad_stride < s.grad_offset + s.width || s.grad_offset < 0 ||
+        if (s.step < 1 || s.rows < 0 || s.width <= 0 || s.grad_stride < s.grad_offset + s.width || s.grad_offset < 0 ||
             s.param_stride < s.param_offset + s.width || s.param_offset < 0)
             return PXB_ERR_BAD_ARG;
         if (s.rows > 0 && (!s.param || !s.grad || !s.exp_avg || !s.exp_avg_sq)) return PXB_ERR_BAD_ARG;
@@ -145,7 +144,9 @@ extern "C" int pxb_adam_densify_step(const pxb_adam_group* groups, int n_groups,
         G.n = s.rows * s.width;
         G.width = s.width; G.p_stride = s.param_stride; G.p_off = s.param_offset;
         G.g_stride = s.grad_stride; G.g_off = s.grad_offset;
+        const double bc1 = 1.0 - pow(beta1, (double)s.step), bc2 = 1.0 - pow(beta2, (double)s.step);
         G.step_size = (float)(s.lr / bc1);
+        G.inv_bc2_sqrt = (float)(1.0 / sqrt(bc2));
         G.cta_begin = (int)cta;
         cta += (G.n + kOptChunk - 1) / kOptChunk;
     }

@@ -58,7 +58,7 @@ class DensificationStats:
     def preprocess(self, uv_points: Union[Tensor, Sequence[Tensor]], visibility: Optional[Tensor], radii: Tensor) -> None:
         """``DensificationController.preprocess(uv_points=..., visibility=..., radii=...)``: the statistics alone
         (use :meth:`GaussianAdam.step` with ``stats=`` to fold them into the optimizer launch)."""
-        _launch_step([], 0.9, 0.999, 1e-15, 1, self, viewspace_grad(uv_points), radii)
+        _launch_step([], 0.9, 0.999, 1e-15, self, viewspace_grad(uv_points), radii)
 
 
 def viewspace_grad(uv_points: Union[Tensor, Sequence[Tensor]]) -> Tensor:
@@ -72,7 +72,7 @@ def viewspace_grad(uv_points: Union[Tensor, Sequence[Tensor]]) -> Tensor:
     return grads[0] if len(grads) == 1 else torch.stack(grads, 0).sum(0)
 
 
-def _launch_step(groups: List[_lib.AdamGroup], beta1, beta2, eps, step, stats: Optional[DensificationStats],
+def _launch_step(groups: List[_lib.AdamGroup], beta1, beta2, eps, stats: Optional[DensificationStats],
                  ndc_grad: Optional[Tensor], radii: Optional[Tensor]) -> None:
     arr = (_lib.AdamGroup * max(len(groups), 1))(*groups)
     if stats is not None:
@@ -97,7 +97,7 @@ def _launch_step(groups: List[_lib.AdamGroup], beta1, beta2, eps, step, stats: O
         keep = ()
     with torch.cuda.device(dev):
         _lib.launch("pxb_adam_densify_step", C.cast(arr, C.c_void_p), len(groups), float(beta1), float(beta2), float(eps),
-                    int(step), *tail, _stream(dev))
+                    *tail, _stream(dev))
     del keep
 
 
@@ -116,7 +116,7 @@ class GaussianAdam:
         self.params = dict(params)
         self.lrs = dict(DEFAULT_LRS if lrs is None else lrs)
         self.betas, self.eps = (float(betas[0]), float(betas[1])), float(eps)
-        self.step_count = 0
+        self.steps: Dict[str, int] = {k: 0 for k in self.params}  # per parameter, as torch.optim keeps them
         self.state: Dict[str, Dict[str, Tensor]] = {}
         for k, p in self.params.items():
             _cuda(p, k)
@@ -143,7 +143,7 @@ class GaussianAdam:
 
     def state_dict(self) -> dict:
         names = list(self.params)
-        return {"state": {i: {"step": torch.tensor(float(self.step_count)), "exp_avg": self.state[k]["exp_avg"],
+        return {"state": {i: {"step": torch.tensor(float(self.steps[k])), "exp_avg": self.state[k]["exp_avg"],
                               "exp_avg_sq": self.state[k]["exp_avg_sq"]} for i, k in enumerate(names)},
                 "param_groups": [{"name": k, "lr": g["lr"], "betas": self.betas, "eps": self.eps, "params": [i]}
                                  for i, (k, g) in enumerate(zip(names, self.param_groups))]}
@@ -154,7 +154,7 @@ class GaussianAdam:
             st = sd["state"][i]
             self.state[k]["exp_avg"].copy_(st["exp_avg"])
             self.state[k]["exp_avg_sq"].copy_(st["exp_avg_sq"])
-            self.step_count = int(float(st["step"]))
+            self.steps[k] = int(float(st["step"]))
 
     # -- the fused step -----------------------------------------------------------------------------
     def _groups(self, grads: Optional[Dict[str, Tensor]], keep: list) -> List[_lib.AdamGroup]:
@@ -166,6 +166,8 @@ class GaussianAdam:
             if g.dtype != torch.float32 or not g.is_contiguous() or g.shape != p.shape:
                 g = g.float().contiguous().reshape(p.shape)
             keep.append(g)
+            self.steps[k] += 1
+            t = self.steps[k]
             st = self.state[k]
             rows = p.shape[0] if p.dim() > 0 else 1
             width = p.numel() // max(rows, 1)
@@ -173,11 +175,11 @@ class GaussianAdam:
             if k == "shs":
                 # one [P,16,3] leaf, the reference's two groups: the DC row (columns 0..2) trains with the features
                 # learning rate, the higher orders (3..47) with features_rest's
-                out.append(_lib.AdamGroup(*ptrs, rows, 3, width, 0, width, 0, self.lrs["features"]))
+                out.append(_lib.AdamGroup(*ptrs, rows, 3, width, 0, width, 0, t, self.lrs["features"]))
                 if width > 3:
-                    out.append(_lib.AdamGroup(*ptrs, rows, width - 3, width, 3, width, 3, self.lrs["features_rest"]))
+                    out.append(_lib.AdamGroup(*ptrs, rows, width - 3, width, 3, width, 3, t, self.lrs["features_rest"]))
             else:
-                out.append(_lib.AdamGroup(*ptrs, rows, width, width, 0, width, 0, self.lrs[k]))
+                out.append(_lib.AdamGroup(*ptrs, rows, width, width, 0, width, 0, t, self.lrs[k]))
         return out
 
     def step(self, stats: Optional[DensificationStats] = None, uv_points=None, visibility: Optional[Tensor] = None,
@@ -187,9 +189,7 @@ class GaussianAdam:
         ``visibility`` is ``radii > 0`` and is recomputed in the kernel) are updated by the same launch."""
         keep: list = []
         groups = self._groups(grads, keep)
-        if groups:
-            self.step_count += 1
-        _launch_step(groups, self.betas[0], self.betas[1], self.eps, max(self.step_count, 1), stats,
+        _launch_step(groups, self.betas[0], self.betas[1], self.eps, stats,
                      viewspace_grad(uv_points) if stats is not None else None, radii)
 
     def update_model(self, **kwargs) -> None:

@@ -107,9 +107,10 @@ def test_argument_errors_are_return_codes():
     assert L.pxb_fused_backward(10, 3, *([one] * 4), 0, 0, one, one, one, 8, 8, 12, one, one, one, one, one, one, one,
                                 null, null, one, one, one, null) == -1                                 # neither d_shs nor d_rgb
     assert [L.pxb_loss_workspace_bytes(0, 3, 8, 8), L.pxb_loss_workspace_bytes(1, 1, 1, 1)] == [0, 8]
-    grp = (_lib.AdamGroup * 1)(_lib.AdamGroup(16, 16, 16, 16, 10, 3, 3, 0, 2, 0, 1e-3))           # grad_stride < offset + width
-    assert L.pxb_adam_densify_step(C.cast(grp, C.c_void_p), 1, 0.9, 0.999, 1e-15, 1, 0, null, null, 1.0, 1.0, null, null, null, null) == -1
-    assert L.pxb_adam_densify_step(null, 9, 0.9, 0.999, 1e-15, 1, 0, null, null, 1.0, 1.0, null, null, null, null) == -1    # > 8 groups
-    assert L.pxb_adam_densify_step(null, 0, 0.9, 0.999, 1e-15, 0, 0, null, null, 1.0, 1.0, null, null, null, null) == -1    # step < 1
-    assert L.pxb_adam_densify_step(null, 0, 0.9, 0.999, 1e-15, 1, 5, one, null, 1.0, 1.0, one, one, one, null) == -1        # no radii
-    assert L.pxb_adam_densify_step(null, 0, 0.9, 0.999, 1e-15, 1, 0, null, null, 1.0, 1.0, null, null, null, null) == 0     # nothing to do
+    grp = (_lib.AdamGroup * 1)(_lib.AdamGroup(16, 16, 16, 16, 10, 3, 3, 0, 2, 0, 1, 1e-3))        # grad_stride < offset + width
+    assert L.pxb_adam_densify_step(C.cast(grp, C.c_void_p), 1, 0.9, 0.999, 1e-15, 0, null, null, 1.0, 1.0, null, null, null, null) == -1
+    grp = (_lib.AdamGroup * 1)(_lib.AdamGroup(16, 16, 16, 16, 10, 3, 3, 0, 3, 0, 0, 1e-3))        # step < 1
+    assert L.pxb_adam_densify_step(C.cast(grp, C.c_void_p), 1, 0.9, 0.999, 1e-15, 0, null, null, 1.0, 1.0, null, null, null, null) == -1
+    assert L.pxb_adam_densify_step(null, 9, 0.9, 0.999, 1e-15, 0, null, null, 1.0, 1.0, null, null, null, null) == -1    # > 8 groups
+    assert L.pxb_adam_densify_step(null, 0, 0.9, 0.999, 1e-15, 5, one, null, 1.0, 1.0, one, one, one, null) == -1        # no radii
+    assert L.pxb_adam_densify_step(null, 0, 0.9, 0.999, 1e-15, 0, null, null, 1.0, 1.0, null, null, null, null) == 0     # nothing to do

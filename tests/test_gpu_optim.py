@@ -68,7 +68,7 @@ def test_adam_matches_torch_optim_adam(OPT, P):
     sd = ours.state_dict()
     again = OPT.GaussianAdam({k: v.detach().clone().requires_grad_() for k, v in gpu.items()})
     again.load_state_dict(sd)
-    assert again.step_count == ours.step_count
+    assert again.steps == ours.steps and ours.steps["opacity"] == 3 and ours.steps["position"] == 4
     assert torch.equal(again.state["scaling"]["exp_avg"], ours.state["scaling"]["exp_avg"])
 
 
@@ -122,7 +122,7 @@ def test_statistics_match_reference_controller_golden_and_fold_into_the_adam_lau
         for name in ("grad_accum", "acc_steps", "max_radii"):
             want = torch.from_numpy(z[f"it{it}_{name}"])
             assert _close(getattr(stats, name), want, 1e-6), (it, name)
-    assert opt.step_count == 2 and float(params["position"].abs().max()) > 0
+    assert opt.steps["position"] == 2 and float(params["position"].abs().max()) > 0
     avg = stats.average_grad()
     assert torch.isfinite(avg).all() and avg.shape == (P, 1)
 
