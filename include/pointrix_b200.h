@@ -119,16 +119,24 @@ int pxb_blend_counters(unsigned long long* counters_dev);
  *      (pointrix/model/renderer/msplat.py:94-139 forward; its autograd graph backward).
  *      shs[P,16,3] (the point cloud's native layout), sh_degree in 0..3,
  *      features = rgb(3) [+ depth] [+ extra[P,n_extra]].
- *      d_cam[19] = dintr[4], dextr[12], dcamera_center[3] (zeroed by caller) or NULL. ---- */
+ *      d_cam[19] = dintr[4], dextr[12], dcamera_center[3] (zeroed by caller) or NULL.
+ *      RAW mode (shs_rest != NULL): the inputs are the point cloud's RAW parameters --
+ *      scales = log-scales, quats = un-normalised quaternions, opacity = logits, shs = features[P,1,3],
+ *      shs_rest = features_rest[P,15,3] -- and exp / normalize / sigmoid / cat
+ *      (pointrix/model/point_cloud/gaussian_points.py:70-86) happen inside the kernels; the backward then
+ *      needs opacity_raw and writes the gradients OF THE RAW TENSORS (d_shs = d_features[P,3],
+ *      d_shs_rest = d_features_rest[P,45]).  shs_rest == NULL: post-activation inputs, as render_iter gets them. ---- */
 int pxb_fused_forward(int P, int sh_degree, const float* pos, const float* scales, const float* quats,
-                      const float* opacity, const float* shs, const float* extra, int n_extra, int with_depth,
-                      const float* intr, const float* extr, const float* cam_center, int W, int H, float nearest,
-                      float extent, int S, int tight, float* rec, float* depth, int* radius, int* tiles, void* stream);
+                      const float* opacity, const float* shs, const float* shs_rest, const float* extra, int n_extra,
+                      int with_depth, const float* intr, const float* extr, const float* cam_center, int W, int H,
+                      float nearest, float extent, int S, int tight, float* rec, float* depth, int* radius, int* tiles,
+                      void* stream);
 int pxb_fused_backward(int P, int sh_degree, const float* pos, const float* scales, const float* quats,
-                       const float* shs, int n_extra, int with_depth, const float* intr, const float* extr,
-                       const float* cam_center, int W, int H, int S, const float* depth, const int* radius,
-                       const float* grec, float* d_pos, float* d_scales, float* d_quats, float* d_opacity,
-                       float* d_shs, float* d_rgb, float* d_extra, float* d_ndc, float* d_cam, void* stream);
+                       const float* opacity_raw, const float* shs, const float* shs_rest, int n_extra, int with_depth,
+                       const float* intr, const float* extr, const float* cam_center, int W, int H, int S,
+                       const float* depth, const int* radius, const float* grec, float* d_pos, float* d_scales,
+                       float* d_quats, float* d_opacity, float* d_shs, float* d_shs_rest, float* d_rgb, float* d_extra,
+                       float* d_ndc, float* d_cam, void* stream);
 
 /* ---- one view of MsplatRender.render_iter behind ONE call each way
  *      (pointrix/model/renderer/msplat.py:94-151 and its autograd graph): pxb_fused_forward (tight
@@ -143,8 +151,8 @@ int pxb_fused_backward(int P, int sh_degree, const float* pos, const float* scal
  *      Saved for the backward: rec[P,S], depth[P], radius[P], idx_sorted, tile_range, final_T, ncontrib. ---- */
 size_t pxb_render_workspace_bytes(int P, long long N_cap, int W, int H);
 int pxb_render_forward(int P, int sh_degree, const float* pos, const float* scales, const float* quats,
-                       const float* opacity, const float* shs, const float* extra, int n_extra, int with_depth,
-                       const float* intr, const float* extr, const float* cam_center, int W, int H, float nearest,
+                       const float* opacity, const float* shs, const float* shs_rest, const float* extra, int n_extra,
+                       int with_depth, const float* intr, const float* extr, const float* cam_center, int W, int H, float nearest,
                        float extent, float bg, int S, long long N_cap, float* rec, float* depth, int* radius,
                        int* idx_sorted, int* tile_range, float* final_T, int* ncontrib, float* out, int* total_host,
                        void* ws, size_t ws_bytes, void* const* stage_events, void* stream);
@@ -154,12 +162,13 @@ int pxb_render_forward(int P, int sh_degree, const float* pos, const float* scal
  * factored form of the SH gradient, d_shs = basis(dir) (x) d_rgb, that pxb_sh_grad_gather sums over the
  * views of a data-parallel step. */
 int pxb_render_backward(int P, int sh_degree, const float* pos, const float* scales, const float* quats,
-                        const float* shs, int n_extra, int with_depth, const float* intr, const float* extr,
-                        const float* cam_center, int W, int H, float bg, int S, const float* rec, const float* depth,
-                        const int* radius, const int* idx_sorted, const int* tile_range, const float* final_T,
-                        const int* ncontrib, const float* dL_dout, float* grec, float* d_pos, float* d_scales,
-                        float* d_quats, float* d_opacity, float* d_shs, float* d_rgb, float* d_extra, float* d_ndc,
-                        float* d_cam, void* const* stage_events, void* stream);
+                        const float* opacity_raw, const float* shs, const float* shs_rest, int n_extra, int with_depth,
+                        const float* intr, const float* extr, const float* cam_center, int W, int H, float bg, int S,
+                        const float* rec, const float* depth, const int* radius, const int* idx_sorted,
+                        const int* tile_range, const float* final_T, const int* ncontrib, const float* dL_dout,
+                        float* grec, float* d_pos, float* d_scales, float* d_quats, float* d_opacity, float* d_shs,
+                        float* d_shs_rest, float* d_rgb, float* d_extra, float* d_ndc, float* d_cam,
+                        void* const* stage_events, void* stream);
 
 /* ---- data-parallel gradient exchange (all-reduce(SUM) of the parameter gradients and
  *      ndc.grad, all-reduce(MAX) of radii; the reference's equivalent is batch_size = world on one GPU,
@@ -209,6 +218,14 @@ int pxb_pixel_loss_forward(int mode, int B, long long n, const float* pred, cons
                            float* mean_out, void* ws, size_t ws_bytes, void* stream);
 int pxb_pixel_loss_backward(int mode, int B, long long n, const float* pred, const float* gt, const float* w,
                             const float* g_map, float* d_pred, void* stream);
+
+/* ---- camera model of one view: replaces CameraModel.extrinsic_matrices / camera_centers
+ *      (pointrix/model/camera/camera_model.py:92-175; unitquat_to_rotmat, pointrix/utils/pose.py:40-83).
+ *      qrot[4] (w first, any norm: normalised inside), tvec[3] -> extrinsic[4,4] = [R | t; 0 0 0 1], center[3] = -R^T t.
+ *      Backward: d_extrinsic[4,4] and / or d_center[3] (either may be NULL) -> d_qrot[4], d_tvec[3]. ---- */
+int pxb_camera_forward(const float* qrot, const float* tvec, float* extrinsic, float* center, void* stream);
+int pxb_camera_backward(const float* qrot, const float* tvec, const float* d_extrinsic, const float* d_center,
+                        float* d_qrot, float* d_tvec, void* stream);
 
 /* ---- optimizer step + densification statistics on the Gaussian table: replaces
  *      torch.optim.Adam.step as driven by BaseOptimizer.update_model (pointrix/optimizer/optimizer.py:128-140;

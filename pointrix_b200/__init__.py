@@ -17,9 +17,9 @@ from . import io  # noqa: F401  (.ply / .pth formats of the Gaussian table, poin
 from . import loss  # noqa: F401  (l1_loss / l2_loss / psnr / ssim / l1_ssim_loss, pointrix/model/loss.py)
 from . import optim  # noqa: F401  (fused Adam + densification statistics, pointrix/optimizer/optimizer.py, controller/gs.py)
 from .registry import RENDERER_REGISTRY, parse_renderer  # noqa: F401
-from .renderer import MsplatRender, RenderFeatures, fused_render  # noqa: F401
+from .renderer import MsplatRender, RenderFeatures, camera_extrinsics, fused_render  # noqa: F401
 
 __all__ = [
     "project_point", "compute_cov3d", "ewa_project", "sort_gaussian", "compute_sh", "alpha_blending",
-    "rasterization", "MsplatRender", "RenderFeatures", "RENDERER_REGISTRY", "parse_renderer", "fused_render", "loss", "io", "optim",
+    "rasterization", "MsplatRender", "RenderFeatures", "RENDERER_REGISTRY", "parse_renderer", "fused_render", "camera_extrinsics", "loss", "io", "optim",
 ]

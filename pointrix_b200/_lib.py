@@ -50,22 +50,24 @@ SIGNATURES = {
     "pxb_blend_forward": (i32, [p, i32, i32, p, p, f32, i32, i32, p, p, p, p]),
     "pxb_blend_backward": (i32, [p, i32, i32, p, p, f32, i32, i32, p, p, p, p, p]),
     "pxb_blend_counters": (i32, [p]),
-    "pxb_fused_forward": (i32, [i32, i32, p, p, p, p, p, p, i32, i32, p, p, p, i32, i32, f32, f32, i32, i32, p, p, p, p, p]),
+    "pxb_fused_forward": (i32, [i32, i32, p, p, p, p, p, p, p, i32, i32, p, p, p, i32, i32, f32, f32, i32, i32, p, p, p, p, p]),
     "pxb_render_workspace_bytes": (sz, [i32, i64, i32, i32]),
-    "pxb_render_forward": (i32, [i32, i32, p, p, p, p, p, p, i32, i32, p, p, p, i32, i32, f32, f32, f32, i32, i64,
+    "pxb_render_forward": (i32, [i32, i32, p, p, p, p, p, p, p, i32, i32, p, p, p, i32, i32, f32, f32, f32, i32, i64,
                                  p, p, p, p, p, p, p, p, p, p, sz, p, p]),
-    "pxb_render_backward": (i32, [i32, i32, p, p, p, p, i32, i32, p, p, p, i32, i32, f32, i32, p, p, p, p, p, p, p,
-                                  p, p, p, p, p, p, p, p, p, p, p, p, p]),
+    "pxb_render_backward": (i32, [i32, i32, p, p, p, p, p, p, i32, i32, p, p, p, i32, i32, f32, i32, p, p, p, p, p, p, p,
+                                  p, p, p, p, p, p, p, p, p, p, p, p, p, p]),
     "pxb_nvls_allreduce": (i32, [p, i64, i64, i32, i32, p]),
     "pxb_p2p_allreduce": (i32, [p, i64, i64, i32, i32, p]),
     "pxb_sh_grad_gather": (i32, [p, i64, i64, i32, i32, i32, p, p, p]),
-    "pxb_fused_backward": (i32, [i32, i32, p, p, p, p, i32, i32, p, p, p, i32, i32, i32, p, p, p, p, p, p, p, p, p, p, p, p, p]),
+    "pxb_fused_backward": (i32, [i32, i32, p, p, p, p, p, p, i32, i32, p, p, p, i32, i32, i32, p, p, p, p, p, p, p, p, p, p, p, p, p, p]),
     "pxb_loss_workspace_bytes": (sz, [i32, i32, i32, i32]),
     "pxb_l1_ssim_forward": (i32, [i32, i32, i32, i32, p, p, p, p, p, p, sz, p]),
     "pxb_l1_ssim_loss_forward": (i32, [i32, i32, i32, i32, p, p, f32, p, p, p, sz, p]),
     "pxb_l1_ssim_backward": (i32, [i32, i32, i32, i32, p, p, p, p, p, i32, f32, f32, p, p]),
     "pxb_pixel_loss_forward": (i32, [i32, i32, i64, p, p, p, p, p, sz, p]),
     "pxb_pixel_loss_backward": (i32, [i32, i32, i64, p, p, p, p, p, p]),
+    "pxb_camera_forward": (i32, [p, p, p, p, p]),
+    "pxb_camera_backward": (i32, [p, p, p, p, p, p, p]),
     "pxb_adam_densify_step": (i32, [p, i32, f64, f64, f64, i32, p, p, f32, f32, p, p, p, p]),
 }
 

@@ -16,7 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 PKG = os.path.dirname(HERE)
 ROOT = os.path.dirname(PKG)
 LIB = os.path.join(PKG, "libpointrix_b200.so")
-SOURCES = ["preprocess.cu", "binning.cu", "blend.cu", "exchange.cu", "pipeline.cu", "loss.cu", "optim.cu"]
+SOURCES = ["preprocess.cu", "binning.cu", "blend.cu", "exchange.cu", "pipeline.cu", "loss.cu", "optim.cu", "camera.cu"]
 HEADERS = ["common.cuh", "sh.cuh", os.path.join(ROOT, "include", "pointrix_b200.h")]
 
 NVCC_FLAGS = [

@@ -287,7 +287,8 @@ inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, siz
 //                    pinned, device-mapped host word total_host (nullable); rect: the fused forward's tile
 //                    rectangles {x0 | y0 << 16, w | h << 16} (nullable: recomputed from uv / radius)
 int fused_forward(int P, int sh_degree, const float* pos, const float* scales, const float* quats, const float* opacity,
-                  const float* shs, const float* extra, int n_extra, int with_depth, const float* intr, const float* extr,
+                  const float* shs, const float* shs_rest, const float* extra, int n_extra, int with_depth, const float* intr,
+                  const float* extr,
                   const float* cam_center, int W, int H, float nearest, float extent, int S, int tight, float* rec,
                   float* depth, int* radius, int* tiles, int* rect /*int2[P], nullable*/, unsigned int* vis_cnt /*nullable*/,
                   void* stream);

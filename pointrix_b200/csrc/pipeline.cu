@@ -58,7 +58,8 @@ size_t pxb_render_workspace_bytes(int P, long long N_cap, int W, int H) {
 }
 
 int pxb_render_forward(int P, int sh_degree, const float* pos, const float* scales, const float* quats,
-                       const float* opacity, const float* shs, const float* extra, int n_extra, int with_depth,
+                       const float* opacity, const float* shs, const float* shs_rest, const float* extra, int n_extra,
+                       int with_depth,
                        const float* intr, const float* extr, const float* cam_center, int W, int H, float nearest,
                        float extent, float bg, int S, long long N_cap, float* rec, float* depth, int* radius,
                        int* idx_sorted, int* tile_range, float* final_T, int* ncontrib, float* out, int* total_host,
@@ -72,8 +73,8 @@ int pxb_render_forward(int P, int sh_degree, const float* pos, const float* scal
     // the binning counters the fused forward accumulates into (visible Gaussians per 1024 ids) are zeroed first
     if ((rc = bin_clear(P, b.ws_p, b.ws_p_bytes, stream))) return rc;
     if ((rc = mark(stage_events, 0, s))) return rc;
-    rc = fused_forward(P, sh_degree, pos, scales, quats, opacity, shs, extra, n_extra, with_depth, intr, extr, cam_center,
-                       W, H, nearest, extent, S, /*tight=*/1, rec, depth, radius, b.tiles, b.rect,
+    rc = fused_forward(P, sh_degree, pos, scales, quats, opacity, shs, shs_rest, extra, n_extra, with_depth, intr, extr,
+                       cam_center, W, H, nearest, extent, S, /*tight=*/1, rec, depth, radius, b.tiles, b.rect,
                        bin_vis_counters(P, b.ws_p), stream);
     if (rc) return rc;
     if ((rc = mark(stage_events, 1, s))) return rc;
@@ -91,12 +92,13 @@ int pxb_render_forward(int P, int sh_degree, const float* pos, const float* scal
 }
 
 int pxb_render_backward(int P, int sh_degree, const float* pos, const float* scales, const float* quats,
-                        const float* shs, int n_extra, int with_depth, const float* intr, const float* extr,
+                        const float* opacity_raw, const float* shs, const float* shs_rest, int n_extra, int with_depth,
+                        const float* intr, const float* extr,
                         const float* cam_center, int W, int H, float bg, int S, const float* rec, const float* depth,
                         const int* radius, const int* idx_sorted, const int* tile_range, const float* final_T,
                         const int* ncontrib, const float* dL_dout, float* grec, float* d_pos, float* d_scales,
-                        float* d_quats, float* d_opacity, float* d_shs, float* d_rgb, float* d_extra, float* d_ndc,
-                        float* d_cam, void* const* stage_events, void* stream) {
+                        float* d_quats, float* d_opacity, float* d_shs, float* d_shs_rest, float* d_rgb, float* d_extra,
+                        float* d_ndc, float* d_cam, void* const* stage_events, void* stream) {
     cudaStream_t s = (cudaStream_t)stream;
     const int C = 3 + (with_depth ? 1 : 0) + n_extra;
     if (P <= 0 || W <= 0 || H <= 0) return PXB_ERR_BAD_ARG;
@@ -107,9 +109,9 @@ int pxb_render_backward(int P, int sh_degree, const float* pos, const float* sca
     rc = pxb_blend_backward(rec, S, C, idx_sorted, tile_range, bg, W, H, final_T, ncontrib, dL_dout, grec, stream);
     if (rc) return rc;
     if ((rc = mark(stage_events, 1, s))) return rc;
-    rc = pxb_fused_backward(P, sh_degree, pos, scales, quats, shs, n_extra, with_depth, intr, extr, cam_center, W, H, S,
-                            depth, radius, grec, d_pos, d_scales, d_quats, d_opacity, d_shs, d_rgb, d_extra, d_ndc,
-                            d_cam, stream);
+    rc = pxb_fused_backward(P, sh_degree, pos, scales, quats, opacity_raw, shs, shs_rest, n_extra, with_depth, intr, extr,
+                            cam_center, W, H, S, depth, radius, grec, d_pos, d_scales, d_quats, d_opacity, d_shs, d_shs_rest,
+                            d_rgb, d_extra, d_ndc, d_cam, stream);
     if (rc) return rc;
     return mark(stage_events, 2, s);
 }

@@ -422,12 +422,59 @@ __device__ __forceinline__ void stage_sh_rows(float* warp_smem, const float* __r
     }
 }
 
-template <int KA>  // active SH basis count: 1,4,9,16
+// ---- parameter activations folded into the fused kernels (RAW = true) -------------------
+// The point cloud stores log-scales, un-normalised quaternions, opacity logits and the SH coefficients as two
+// tensors features[P,1,3] / features_rest[P,15,3]; every iteration the reference materialises exp / normalize /
+// sigmoid / cat of them before the renderer (pointrix/model/point_cloud/gaussian_points.py:70-86,
+// base_model.py:79-85) and their gradients behind it.  With RAW the fused forward reads the raw tensors and
+// activates in registers, and the fused backward emits the gradients of the raw tensors.
+// expf_acc: accurate exponential (the TU is compiled with --use_fast_math, which maps expf to ex2.approx).
+extern "C" __device__ float __nv_expf(float);  // libdevice's accurate expf (what torch.exp evaluates per element)
+__device__ __forceinline__ float expf_acc(float x) { return __nv_expf(x); }
+__device__ __forceinline__ float sigmoid_acc(float x) { return __fdiv_rn(1.0f, 1.0f + expf_acc(-x)); }
+// F.normalize(q, dim = 1): q / max(||q||, 1e-12); returns 1 / max(||q||, eps)
+__device__ __forceinline__ float4 normalize_quat(float4 q, float& inv_n) {
+    const float n = __fsqrt_rn(q.x * q.x + q.y * q.y + q.z * q.z + q.w * q.w);
+    inv_n = __fdiv_rn(1.0f, fmaxf(n, 1e-12f));
+    return make_float4(q.x * inv_n, q.y * inv_n, q.z * inv_n, q.w * inv_n);
+}
+
+constexpr int kRestRow = 45;  // floats per features_rest row (15 coefficients x 3 channels)
+// Stage this warp's 32 features_rest rows (contiguous: 1440 floats) and 32 features rows (96 floats) with flat
+// 16-byte cp.async copies.  Layout in the warp's staging area: rest at [0, 1440), DC at [1440, 1536).
+// Lane l then reads row l with scalar loads at stride 45 / 3 words (odd strides: conflict free).
+__device__ __forceinline__ void stage_raw_sh(float* warp_smem, const float* __restrict__ features,
+                                             const float* __restrict__ features_rest, int g0, int P, int k_active) {
+    const int lane = threadIdx.x & 31;
+    const int rows = min(32, P - g0);
+    if (rows <= 0) return;
+    if (k_active > 1) {
+        const int n = rows * kRestRow;
+        const float* src = features_rest + (size_t)g0 * kRestRow;
+        for (int f = lane * 4; f < n; f += 128) {
+            if (f + 4 <= n) cp_async16(warp_smem + f, src + f);
+            else for (int e = f; e < n; e++) warp_smem[e] = src[e];
+        }
+    }
+    const int n = rows * 3;
+    const float* src = features + (size_t)g0 * 3;
+    for (int f = lane * 4; f < n; f += 128) {
+        if (f + 4 <= n) cp_async16(warp_smem + 32 * kRestRow + f, src + f);
+        else for (int e = f; e < n; e++) warp_smem[32 * kRestRow + e] = src[e];
+    }
+}
+// SH coefficient (k, ch) of this lane's Gaussian from the raw staging area
+__device__ __forceinline__ float raw_sh(const float* warp_smem, int lane, int k, int ch) {
+    return k == 0 ? warp_smem[32 * kRestRow + 3 * lane + ch] : warp_smem[kRestRow * lane + 3 * (k - 1) + ch];
+}
+
+template <int KA, bool RAW>  // KA: active SH basis count 1,4,9,16; RAW: inputs are the point cloud's raw parameters
 __global__ void __launch_bounds__(kFThreads)
 fused_fwd_kernel(int P, const float* __restrict__ pos, const float* __restrict__ scales,
                  const float4* __restrict__ quats, const float* __restrict__ opacity,
-                 const float* __restrict__ shs /*[P,16,3]*/, const float* __restrict__ extra, int n_extra,
-                 int with_depth, const float* __restrict__ intr, const float* __restrict__ extr,
+                 const float* __restrict__ shs /*[P,16,3]; RAW: features[P,1,3]*/,
+                 const float* __restrict__ shs_rest /*RAW: features_rest[P,15,3]*/, const float* __restrict__ extra,
+                 int n_extra, int with_depth, const float* __restrict__ intr, const float* __restrict__ extr,
                  const float* __restrict__ cam_center, int W, int H, int gx, int gy, float nearest,
                  float extent, int S, int tight, float* __restrict__ rec, float* __restrict__ depth,
                  int* __restrict__ radius, int* __restrict__ tiles, int2* __restrict__ rect /*nullable*/,
@@ -438,7 +485,8 @@ fused_fwd_kernel(int P, const float* __restrict__ pos, const float* __restrict__
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     float* wsm = sh_smem + warp * 32 * kShPitch;
     constexpr int NQ = (3 * KA + 3) / 4;
-    stage_sh_rows(wsm, shs, blockIdx.x * blockDim.x + warp * 32, P, NQ);
+    if (RAW) stage_raw_sh(wsm, shs, shs_rest, blockIdx.x * blockDim.x + warp * 32, P, KA);
+    else stage_sh_rows(wsm, shs, blockIdx.x * blockDim.x + warp * 32, P, NQ);
 
     const Cam c = load_cam(intr, extr);
     float px = 0.f, py = 0.f, pz = 0.f;
@@ -452,9 +500,15 @@ fused_fwd_kernel(int P, const float* __restrict__ pos, const float* __restrict__
         keep = project_uv(c, t, W, H, nearest, extent, u, v);
         keep = keep && (t.z != 0.f);  // visible = depth != 0 (msplat.py:115)
         if (keep) {
-            const float4 q = quats[i];
+            float4 q = quats[i];
+            float sx = scales[3 * i], sy = scales[3 * i + 1], sz = scales[3 * i + 2];
+            if (RAW) {  // gaussian_points.py:70-82: scaling = exp, rotation = normalize
+                float inv_n;
+                q = normalize_quat(q, inv_n);
+                sx = expf_acc(sx); sy = expf_acc(sy); sz = expf_acc(sz);
+            }
             float cov[6];
-            cov3d_from_scale_quat(scales[3 * i], scales[3 * i + 1], scales[3 * i + 2], q.x, q.y, q.z, q.w, cov);
+            cov3d_from_scale_quat(sx, sy, sz, q.x, q.y, q.z, q.w, cov);
             const EwaT T = ewa_T(c, t);
             float a, b, cc, det;
             ewa_cov2d(T, cov, a, b, cc);
@@ -467,7 +521,8 @@ fused_fwd_kernel(int P, const float* __restrict__ pos, const float* __restrict__
     }
     // the tile rectangle binning will expand -- computed ONCE, here: the key emission reads it back instead of
     // re-deriving it (tight: only the tiles the alpha >= 1/255 ellipse can reach, common.cuh)
-    const float op_i = i < P ? opacity[i] : 0.f;
+    float op_i = i < P ? opacity[i] : 0.f;
+    if (RAW) op_i = sigmoid_acc(op_i);  // gaussian_points.py:66-68
     int2 rc = make_int2(0, 0);
     if (rad > 0) {
         int x0, y0, x1, y1;
@@ -495,10 +550,17 @@ fused_fwd_kernel(int P, const float* __restrict__ pos, const float* __restrict__
         const float* row = wsm + lane * kShPitch;
         float acc[3] = {0.f, 0.f, 0.f};
         float w[4 * NQ];
+        if (RAW) {
 #pragma unroll
-        for (int q = 0; q < NQ; q++) {
-            const float4 f = *reinterpret_cast<const float4*>(row + 4 * q);
-            w[4 * q] = f.x; w[4 * q + 1] = f.y; w[4 * q + 2] = f.z; w[4 * q + 3] = f.w;
+            for (int k = 0; k < KA; k++)
+#pragma unroll
+                for (int ch = 0; ch < 3; ch++) w[3 * k + ch] = raw_sh(wsm, lane, k, ch);
+        } else {
+#pragma unroll
+            for (int q = 0; q < NQ; q++) {
+                const float4 f = *reinterpret_cast<const float4*>(row + 4 * q);
+                w[4 * q] = f.x; w[4 * q + 1] = f.y; w[4 * q + 2] = f.z; w[4 * q + 3] = f.w;
+            }
         }
 #pragma unroll
         for (int k = 0; k < KA; k++) {
@@ -538,15 +600,18 @@ fused_fwd_kernel(int P, const float* __restrict__ pos, const float* __restrict__
 //   opacity, shs (clamp- and degree-masked), extra features
 //   ndc.grad  = duv * (W/2, H/2)                (msplat/msplat/alpha_blending.py:106-110)
 //   camera: dintr[4], dextr[12], dcam_center[3] block-reduced then atomically added.
-template <int KA, int MINB>  // MINB: resident CTAs per SM the register allocation aims for
+template <int KA, int MINB, bool RAW>  // MINB: resident CTAs per SM the register allocation aims for; RAW: see above
 __global__ void __launch_bounds__(kFThreads, MINB)
 fused_bwd_kernel(int P, const float* __restrict__ pos, const float* __restrict__ scales,
-                 const float4* __restrict__ quats, const float* __restrict__ shs, int n_extra, int with_depth,
+                 const float4* __restrict__ quats, const float* __restrict__ opacity /*RAW only: the logits*/,
+                 const float* __restrict__ shs, const float* __restrict__ shs_rest /*RAW: features_rest*/, int n_extra,
+                 int with_depth,
                  const float* __restrict__ intr, const float* __restrict__ extr,
                  const float* __restrict__ cam_center, int W, int H, int S, const float* __restrict__ depth,
                  const int* __restrict__ radius, const float* __restrict__ grec, float* __restrict__ d_pos,
                  float* __restrict__ d_scales, float4* __restrict__ d_quats, float* __restrict__ d_opacity,
-                 float* __restrict__ d_shs, float* __restrict__ d_rgb /*[P,3] or null*/, float* __restrict__ d_extra,
+                 float* __restrict__ d_shs /*RAW: d_features[P,3]*/, float* __restrict__ d_shs_rest /*RAW: [P,45]*/,
+                 float* __restrict__ d_rgb /*[P,3] or null*/, float* __restrict__ d_extra,
                  float* __restrict__ d_ndc, float* __restrict__ d_cam /*[19]: intr4, extr12, center3 or null*/) {
     pdl_wait();
     extern __shared__ __align__(16) float sh_smem[];
@@ -555,7 +620,8 @@ fused_bwd_kernel(int P, const float* __restrict__ pos, const float* __restrict__
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     float* wsm = sh_smem + warp * 32 * kShPitch;
     constexpr int NQ = (3 * KA + 3) / 4;
-    stage_sh_rows(wsm, shs, blockIdx.x * blockDim.x + warp * 32, P, NQ);
+    if (RAW) stage_raw_sh(wsm, shs, shs_rest, blockIdx.x * blockDim.x + warp * 32, P, KA);
+    else stage_sh_rows(wsm, shs, blockIdx.x * blockDim.x + warp * 32, P, NQ);
     const Cam c = load_cam(intr, extr);
     float cg[19];
 #pragma unroll
@@ -576,7 +642,12 @@ fused_bwd_kernel(int P, const float* __restrict__ pos, const float* __restrict__
         if (d_extra != nullptr) {
             for (int e = 0; e < n_extra; e++) d_extra[(size_t)i * n_extra + e] = gr[6 + 3 + with_depth + e];
         }
-        d_opacity[i] = g[5];
+        if (RAW) {  // sigmoid': s (1 - s)
+            const float sg = sigmoid_acc(opacity[i]);
+            d_opacity[i] = g[5] * sg * (1.0f - sg);
+        } else {
+            d_opacity[i] = g[5];
+        }
         d_ndc[2 * i] = g[0] * (0.5f * (float)W);
         d_ndc[2 * i + 1] = g[1] * (0.5f * (float)H);
         const float dep = depth[i];
@@ -593,8 +664,13 @@ fused_bwd_kernel(int P, const float* __restrict__ pos, const float* __restrict__
             cg[8] = px * dt.y; cg[9] = py * dt.y; cg[10] = pz * dt.y; cg[11] = dt.y;
             cg[12] = px * dt.z; cg[13] = py * dt.z; cg[14] = pz * dt.z; cg[15] = dt.z;
             if (radius[i] > 0) {
-                const float4 q = quats[i];
-                const float sx = scales[3 * i], sy = scales[3 * i + 1], sz = scales[3 * i + 2];
+                float4 q = quats[i];
+                float sx = scales[3 * i], sy = scales[3 * i + 1], sz = scales[3 * i + 2];
+                float inv_n = 1.0f;
+                if (RAW) {
+                    q = normalize_quat(q, inv_n);
+                    sx = expf_acc(sx); sy = expf_acc(sy); sz = expf_acc(sz);
+                }
                 float cov[6];
                 cov3d_from_scale_quat(sx, sy, sz, q.x, q.y, q.z, q.w, cov);
                 const float dcn[3] = {g[2], g[3], g[4]};
@@ -608,6 +684,13 @@ fused_bwd_kernel(int P, const float* __restrict__ pos, const float* __restrict__
 #pragma unroll
                     for (int k = 0; k < 12; k++) cg[4 + k] += cgl[2 + k];
                     cov3d_backward(sx, sy, sz, q.x, q.y, q.z, q.w, dV, ds, dq);
+                    if (RAW) {
+                        // exp': d/draw = d/ds * s;  normalize': (dq - q <q, dq>) / ||raw||
+                        ds[0] *= sx; ds[1] *= sy; ds[2] *= sz;
+                        const float dot = q.x * dq[0] + q.y * dq[1] + q.z * dq[2] + q.w * dq[3];
+                        dq[0] = (dq[0] - q.x * dot) * inv_n; dq[1] = (dq[1] - q.y * dot) * inv_n;
+                        dq[2] = (dq[2] - q.z * dot) * inv_n; dq[3] = (dq[3] - q.w * dot) * inv_n;
+                    }
                 }
             }
         }
@@ -626,10 +709,17 @@ fused_bwd_kernel(int P, const float* __restrict__ pos, const float* __restrict__
         sh_basis_grad<KA>(dx, dy, dz, bx, by, bz);
         const float* row = wsm + lane * kShPitch;
         float w[4 * NQ];
+        if (RAW) {
 #pragma unroll
-        for (int q = 0; q < NQ; q++) {
-            const float4 f = *reinterpret_cast<const float4*>(row + 4 * q);
-            w[4 * q] = f.x; w[4 * q + 1] = f.y; w[4 * q + 2] = f.z; w[4 * q + 3] = f.w;
+            for (int k = 0; k < KA; k++)
+#pragma unroll
+                for (int ch = 0; ch < 3; ch++) w[3 * k + ch] = raw_sh(wsm, lane, k, ch);
+        } else {
+#pragma unroll
+            for (int q = 0; q < NQ; q++) {
+                const float4 f = *reinterpret_cast<const float4*>(row + 4 * q);
+                w[4 * q] = f.x; w[4 * q + 1] = f.y; w[4 * q + 2] = f.z; w[4 * q + 3] = f.w;
+            }
         }
         float acc[3] = {0.f, 0.f, 0.f};
 #pragma unroll
@@ -660,6 +750,9 @@ fused_bwd_kernel(int P, const float* __restrict__ pos, const float* __restrict__
             // factored form for the data-parallel exchange (exchange.cu, sh_grad_gather_kernel): dL/dshs of
             // this view is the outer product basis(dir) x gated dL/drgb, so only the 3-vector leaves the kernel
             d_rgb[3 * i] = gr3[0]; d_rgb[3 * i + 1] = gr3[1]; d_rgb[3 * i + 2] = gr3[2];
+        } else if (RAW) {
+            // two outputs: d_features[P,3] directly, d_features_rest[P,45] through the staging area (below)
+            d_shs[3 * i] = o[0]; d_shs[3 * i + 1] = o[1]; d_shs[3 * i + 2] = o[2];
         } else {
             float4* dst = reinterpret_cast<float4*>(d_shs + (size_t)i * 48);
 #pragma unroll
@@ -673,6 +766,24 @@ fused_bwd_kernel(int P, const float* __restrict__ pos, const float* __restrict__
         d_pos[3 * i] = gpos[0]; d_pos[3 * i + 1] = gpos[1]; d_pos[3 * i + 2] = gpos[2];
         d_scales[3 * i] = ds[0]; d_scales[3 * i + 1] = ds[1]; d_scales[3 * i + 2] = ds[2];
         d_quats[i] = make_float4(dq[0], dq[1], dq[2], dq[3]);
+        if (RAW && d_rgb == nullptr) {
+            // this lane's features_rest gradient row into the staging area (every active lane has read its
+            // coefficients out of it by now), conflict free at stride 45
+            __syncwarp(__activemask());
+#pragma unroll
+            for (int j = 0; j < kRestRow; j++) wsm[kRestRow * lane + j] = o[3 + j];
+        }
+    }
+    if (RAW && d_rgb == nullptr) {
+        // the warp's 32 rows are contiguous in d_features_rest: flat, coalesced 16-byte stores
+        __syncwarp();
+        const int g0 = blockIdx.x * blockDim.x + warp * 32;
+        const int n = min(32, P - g0) * kRestRow;
+        float* dst = d_shs_rest + (size_t)g0 * kRestRow;
+        for (int f = lane * 4; f < n; f += 128) {
+            if (f + 4 <= n) *reinterpret_cast<float4*>(dst + f) = *reinterpret_cast<const float4*>(wsm + f);
+            else for (int e = f; e < n; e++) dst[e] = wsm[e];
+        }
     }
     if (d_cam != nullptr) block_reduce_atomic<19>(cg, d_cam, red);
 }
@@ -892,17 +1003,20 @@ int pxb_init(void) {
 }
 
 int pxb_fused_forward(int P, int sh_degree, const float* pos, const float* scales, const float* quats,
-                      const float* opacity, const float* shs, const float* extra, int n_extra, int with_depth,
-                      const float* intr, const float* extr, const float* cam_center, int W, int H, float nearest,
-                      float extent, int S, int tight, float* rec, float* depth, int* radius, int* tiles, void* stream) {
-    return pxb::fused_forward(P, sh_degree, pos, scales, quats, opacity, shs, extra, n_extra, with_depth, intr, extr,
-                              cam_center, W, H, nearest, extent, S, tight, rec, depth, radius, tiles, nullptr, nullptr, stream);
+                      const float* opacity, const float* shs, const float* shs_rest, const float* extra, int n_extra,
+                      int with_depth, const float* intr, const float* extr, const float* cam_center, int W, int H,
+                      float nearest, float extent, int S, int tight, float* rec, float* depth, int* radius, int* tiles,
+                      void* stream) {
+    return pxb::fused_forward(P, sh_degree, pos, scales, quats, opacity, shs, shs_rest, extra, n_extra, with_depth, intr,
+                              extr, cam_center, W, H, nearest, extent, S, tight, rec, depth, radius, tiles, nullptr, nullptr,
+                              stream);
 }
 
 }  // extern "C"
 
 int pxb::fused_forward(int P, int sh_degree, const float* pos, const float* scales, const float* quats,
-                       const float* opacity, const float* shs, const float* extra, int n_extra, int with_depth,
+                       const float* opacity, const float* shs, const float* shs_rest, const float* extra, int n_extra,
+                       int with_depth,
                        const float* intr, const float* extr, const float* cam_center, int W, int H, float nearest,
                        float extent, int S, int tight, float* rec, float* depth, int* radius, int* tiles, int* rect,
                        unsigned int* vis_cnt, void* stream) {
@@ -915,10 +1029,14 @@ int pxb::fused_forward(int P, int sh_degree, const float* pos, const float* scal
     const int nb = blocks_for(P, kFThreads);
     const size_t smem = (size_t)kFThreads * kShPitch * sizeof(float);
     if (gx > 0xffff || gy > 0x7fff) return PXB_ERR_BAD_ARG;  // the packed rectangle holds 16-bit tile coordinates
-#define PXB_LAUNCH_FWD(KA)                                                                                              \
-    PXB_CUDA_OK(launch_k(fused_fwd_kernel<KA>, dim3(nb), dim3(kFThreads), smem, s, P, pos, scales, (const float4*)quats,   \
-                         opacity, shs, extra, n_extra, with_depth, intr, extr, cam_center, W, H, gx, gy, nearest, extent, \
-                         S, tight, rec, depth, radius, tiles, (int2*)rect, vis_cnt))
+    const bool raw = shs_rest != nullptr;  // the point cloud's raw parameters: activations happen in the kernel
+#define PXB_LAUNCH_FWD_V(KA, RAW)                                                                                        \
+    PXB_CUDA_OK(launch_k(fused_fwd_kernel<KA, RAW>, dim3(nb), dim3(kFThreads), smem, s, P, pos, scales,                   \
+                         (const float4*)quats, opacity, shs, shs_rest, extra, n_extra, with_depth, intr, extr, cam_center, \
+                         W, H, gx, gy, nearest, extent, S, tight, rec, depth, radius, tiles, (int2*)rect, vis_cnt))
+#define PXB_LAUNCH_FWD(KA)                   \
+    if (raw) { PXB_LAUNCH_FWD_V(KA, true); } \
+    else { PXB_LAUNCH_FWD_V(KA, false); }
     switch (sh_degree) {
         case 0: PXB_LAUNCH_FWD(1); break;
         case 1: PXB_LAUNCH_FWD(4); break;
@@ -926,30 +1044,39 @@ int pxb::fused_forward(int P, int sh_degree, const float* pos, const float* scal
         default: PXB_LAUNCH_FWD(16); break;
     }
 #undef PXB_LAUNCH_FWD
+#undef PXB_LAUNCH_FWD_V
     return (int)cudaGetLastError();
 }
 
 extern "C" {
 
 int pxb_fused_backward(int P, int sh_degree, const float* pos, const float* scales, const float* quats,
-                       const float* shs, int n_extra, int with_depth, const float* intr, const float* extr,
-                       const float* cam_center, int W, int H, int S, const float* depth, const int* radius,
-                       const float* grec, float* d_pos, float* d_scales, float* d_quats, float* d_opacity,
-                       float* d_shs, float* d_rgb, float* d_extra, float* d_ndc, float* d_cam, void* stream) {
+                       const float* opacity_raw, const float* shs, const float* shs_rest, int n_extra, int with_depth,
+                       const float* intr, const float* extr, const float* cam_center, int W, int H, int S,
+                       const float* depth, const int* radius, const float* grec, float* d_pos, float* d_scales,
+                       float* d_quats, float* d_opacity, float* d_shs, float* d_shs_rest, float* d_rgb, float* d_extra,
+                       float* d_ndc, float* d_cam, void* stream) {
     if (P <= 0) return 0;
     if (sh_degree < 0 || sh_degree > 3) return PXB_ERR_UNSUPPORTED;
     if (d_shs == nullptr && d_rgb == nullptr) return PXB_ERR_BAD_ARG;
-    if ((((uintptr_t)shs) | ((uintptr_t)grec) | ((uintptr_t)quats) | ((uintptr_t)d_shs) | ((uintptr_t)d_quats)) & 15)
+    const bool raw = shs_rest != nullptr;
+    if (raw && (opacity_raw == nullptr || (d_rgb == nullptr && d_shs_rest == nullptr))) return PXB_ERR_BAD_ARG;
+    if ((((uintptr_t)shs) | ((uintptr_t)shs_rest) | ((uintptr_t)grec) | ((uintptr_t)quats) | ((uintptr_t)d_quats) |
+         ((uintptr_t)d_shs_rest) | (raw ? 0 : (uintptr_t)d_shs)) & 15)
         return PXB_ERR_ALIGN;
     cudaStream_t s = (cudaStream_t)stream;
     const int nb = blocks_for(P, kFThreads);
     const size_t smem = (size_t)kFThreads * kShPitch * sizeof(float);
     // 121 registers (4 CTAs of 128 threads per SM).  Capping at 96 for a fifth CTA was measured: 0.130 vs 0.133 ms,
     // not worth the 52 spilled bytes
-#define PXB_LAUNCH_BWD(KA)                                                                                              \
-    PXB_CUDA_OK(launch_k(fused_bwd_kernel<KA, 4>, dim3(nb), dim3(kFThreads), smem, s, P, pos, scales,                     \
-                         (const float4*)quats, shs, n_extra, with_depth, intr, extr, cam_center, W, H, S, depth, radius,  \
-                         grec, d_pos, d_scales, (float4*)d_quats, d_opacity, d_shs, d_rgb, d_extra, d_ndc, d_cam))
+#define PXB_LAUNCH_BWD_V(KA, RAW)                                                                                       \
+    PXB_CUDA_OK(launch_k(fused_bwd_kernel<KA, 4, RAW>, dim3(nb), dim3(kFThreads), smem, s, P, pos, scales,                \
+                         (const float4*)quats, opacity_raw, shs, shs_rest, n_extra, with_depth, intr, extr, cam_center,  \
+                         W, H, S, depth, radius, grec, d_pos, d_scales, (float4*)d_quats, d_opacity, d_shs, d_shs_rest,  \
+                         d_rgb, d_extra, d_ndc, d_cam))
+#define PXB_LAUNCH_BWD(KA)                   \
+    if (raw) { PXB_LAUNCH_BWD_V(KA, true); } \
+    else { PXB_LAUNCH_BWD_V(KA, false); }
     switch (sh_degree) {
         case 0: PXB_LAUNCH_BWD(1); break;
         case 1: PXB_LAUNCH_BWD(4); break;
@@ -957,6 +1084,7 @@ int pxb_fused_backward(int P, int sh_degree, const float* pos, const float* scal
         default: PXB_LAUNCH_BWD(16); break;
     }
 #undef PXB_LAUNCH_BWD
+#undef PXB_LAUNCH_BWD_V
     return (int)cudaGetLastError();
 }
 

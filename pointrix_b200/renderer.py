@@ -132,10 +132,13 @@ class _FusedRender(torch.autograd.Function):
     One foreign call forward (pxb_render_forward), one backward (pxb_render_backward)."""
 
     @staticmethod
-    def forward(ctx, position, opacity, scaling, rotation, shs, extra, intr, extr, cam_center, ndc, sh_degree, W, H,
-                bg, with_depth, nearest):
+    def forward(ctx, position, opacity, scaling, rotation, shs, shs_rest, extra, intr, extr, cam_center, ndc, sh_degree,
+                W, H, bg, with_depth, nearest):
+        # shs_rest is None: post-activation inputs (render_iter).  Otherwise RAW mode (render_iter_raw): opacity /
+        # scaling / rotation are the point cloud's raw parameters, shs = features[P,1,3], shs_rest = features_rest
         pos, op = _f32(position, "position"), _f32(opacity, "opacity")
         sc, rot, sh = _f32(scaling, "scaling"), _f32(rotation, "rotation"), _f32(shs, "shs")
+        sh_r = _f32(shs_rest, "features_rest") if shs_rest is not None else None
         intr_c, extr_c, cc = _f32(intr, "intrinsic_params"), _f32(extr, "extrinsic_matrix"), _f32(cam_center, "camera_center")
         ex = _f32(extra, "extra features") if extra is not None else None
         dev = pos.device
@@ -171,7 +174,7 @@ class _FusedRender(torch.autograd.Function):
             idx_sorted = E((cap,), dtype=i32, device=dev)
             evs, ev_arr = _stage_events(timer, _FWD_STAGES)
             word.value = -1
-            args = (P, int(sh_degree), _p(pos), _p(sc), _p(rot), _p(op), _p(sh), _p(ex), n_extra, int(with_depth),
+            args = (P, int(sh_degree), _p(pos), _p(sc), _p(rot), _p(op), _p(sh), _p(sh_r), _p(ex), n_extra, int(with_depth),
                     _p(intr_c), _p(extr_c), _p(cc), W, H, float(nearest), 1.3, float(bg), S, cap, _p(rec), _p(depth),
                     _p(radius), _p(idx_sorted), _p(tile_range), _p(final_T), _p(ncontrib), _p(out),
                     host_t.data_ptr(), _p(ws), ws.numel(), ev_arr, stream)
@@ -196,16 +199,20 @@ class _FusedRender(torch.autograd.Function):
             # more intersections than the capacity: the lists were truncated, run again with room
             cap = _CAPACITY[ckey] = int(n * 1.25) + 65536
         ctx.save_for_backward(pos, sc, rot, sh, intr_c, extr_c, cc, rec, depth, radius, idx_sorted, tile_range, final_T,
-                              ncontrib)
+                              ncontrib, *((op, sh_r) if sh_r is not None else ()))
+        ctx.raw = sh_r is not None
         ctx.meta = (int(sh_degree), W, H, float(bg), int(with_depth), n_extra, S, Cc,
-                    intr.shape, extr.shape, cam_center.shape, opacity.shape)
+                    intr.shape, extr.shape, cam_center.shape, opacity.shape, shs.shape,
+                    None if shs_rest is None else shs_rest.shape)
         ctx.mark_non_differentiable(radius)
         return out, radius
 
     @staticmethod
     def backward(ctx, d_out, _d_radius):
-        (pos, sc, rot, sh, intr, extr, cc, rec, depth, radius, idx_sorted, tile_range, final_T, ncontrib) = ctx.saved_tensors
-        sh_degree, W, H, bg, with_depth, n_extra, S, Cc, s_intr, s_extr, s_cc, s_op = ctx.meta
+        saved = ctx.saved_tensors
+        (pos, sc, rot, sh, intr, extr, cc, rec, depth, radius, idx_sorted, tile_range, final_T, ncontrib) = saved[:14]
+        op_raw, sh_r = (saved[14], saved[15]) if ctx.raw else (None, None)
+        sh_degree, W, H, bg, with_depth, n_extra, S, Cc, s_intr, s_extr, s_cc, s_op, s_sh, s_shr = ctx.meta
         dev = pos.device
         P = pos.shape[0]
         g = _f32(d_out, "dL_drendered")
@@ -214,49 +221,94 @@ class _FusedRender(torch.autograd.Function):
         # data-parallel caller exchanges them with a single collective (parallel.allreduce_step); a sink
         # may instead supply the buffers itself (symmetric memory) and ask for the factored SH gradient
         plan = None
-        if _GRAD_SINK is not None and hasattr(_GRAD_SINK, "plan"):
+        if _GRAD_SINK is not None and hasattr(_GRAD_SINK, "plan") and not ctx.raw:
             plan = _GRAD_SINK.plan(P, dev, cc, sh_degree)
+        d_sh_rest = None
         if plan is not None:
             d_sh, d_rot, d_pos, d_sc, d_op, d_ndc, d_rgb = plan
         else:
-            flat = _GRAD_SINK.next_buffer(61 * P) if _GRAD_SINK is not None else None
+            flat = _GRAD_SINK.next_buffer(61 * P) if (_GRAD_SINK is not None and not ctx.raw) else None
             if flat is None or flat.device != dev:
-                flat = torch.empty(61 * P, dtype=torch.float32, device=dev)
-            d_sh = flat[0:48 * P].view(P, 16, 3)
-            d_rot = flat[48 * P:52 * P].view(P, 4)
-            d_pos = flat[52 * P:55 * P].view(P, 3)
-            d_sc = flat[55 * P:58 * P].view(P, 3)
-            d_op = flat[58 * P:59 * P]
-            d_ndc = flat[59 * P:61 * P].view(P, 2)
+                flat = torch.empty(61 * P + 4, dtype=torch.float32, device=dev)
+            if ctx.raw:
+                # [features_rest 45P | pad to 4 | rotation 4P | features 3P | position 3P | scaling 3P | opacity P | ndc 2P]
+                o = (45 * P + 3) // 4 * 4
+                d_sh_rest = flat[0:45 * P].view(s_shr)
+                d_rot = flat[o:o + 4 * P].view(P, 4)
+                d_sh = flat[o + 4 * P:o + 7 * P].view(s_sh)
+                o += 7 * P
+            else:
+                d_sh = flat[0:48 * P].view(P, 16, 3)
+                d_rot = flat[48 * P:52 * P].view(P, 4)
+                o = 52 * P
+            d_pos = flat[o:o + 3 * P].view(P, 3)
+            d_sc = flat[o + 3 * P:o + 6 * P].view(P, 3)
+            d_op = flat[o + 6 * P:o + 7 * P]
+            d_ndc = flat[o + 7 * P:o + 9 * P].view(P, 2)
             d_rgb = None
         d_extra = torch.empty(P, n_extra, dtype=torch.float32, device=dev) if n_extra > 0 else None
-        need_cam = any(ctx.needs_input_grad[6:9])
+        need_cam = any(ctx.needs_input_grad[7:10])
         d_cam = torch.empty(19, dtype=torch.float32, device=dev) if need_cam else None
         timer = _lib._timer
         with torch.cuda.device(dev):
             evs, ev_arr = _stage_events(timer, _BWD_STAGES)
             _lib.check(lib.pxb_render_backward(
-                P, sh_degree, _p(pos), _p(sc), _p(rot), _p(sh), n_extra, with_depth, _p(intr), _p(extr), _p(cc), W, H, bg,
-                S, _p(rec), _p(depth), _p(radius), _p(idx_sorted), _p(tile_range), _p(final_T), _p(ncontrib), _p(g),
-                _p(grec), _p(d_pos), _p(d_sc), _p(d_rot), _p(d_op), _p(None if d_rgb is not None else d_sh), _p(d_rgb),
-                _p(d_extra), _p(d_ndc), _p(d_cam), ev_arr, _raw_stream(dev.index)), "pxb_render_backward")
+                P, sh_degree, _p(pos), _p(sc), _p(rot), _p(op_raw), _p(sh), _p(sh_r), n_extra, with_depth, _p(intr), _p(extr),
+                _p(cc), W, H, bg, S, _p(rec), _p(depth), _p(radius), _p(idx_sorted), _p(tile_range), _p(final_T),
+                _p(ncontrib), _p(g), _p(grec), _p(d_pos), _p(d_sc), _p(d_rot), _p(d_op),
+                _p(None if d_rgb is not None else d_sh), _p(d_sh_rest), _p(d_rgb), _p(d_extra), _p(d_ndc), _p(d_cam), ev_arr,
+                _raw_stream(dev.index)), "pxb_render_backward")
         _lib.count_launches("pxb_render_backward", W, H)
         if evs is not None:
             for k, name in enumerate(_BWD_STAGES):
                 if timer.wants(name):
                     timer.events.append((name, evs[k], evs[k + 1]))
-        d_intr = d_cam[0:4].reshape(s_intr) if ctx.needs_input_grad[6] else None
-        d_extr = d_cam[4:16].reshape(s_extr) if ctx.needs_input_grad[7] else None
-        d_cc = d_cam[16:19].reshape(s_cc) if ctx.needs_input_grad[8] else None
-        return (d_pos, d_op.reshape(s_op), d_sc, d_rot, d_sh, d_extra, d_intr, d_extr, d_cc, d_ndc,
+        d_intr = d_cam[0:4].reshape(s_intr) if ctx.needs_input_grad[7] else None
+        d_extr = d_cam[4:16].reshape(s_extr) if ctx.needs_input_grad[8] else None
+        d_cc = d_cam[16:19].reshape(s_cc) if ctx.needs_input_grad[9] else None
+        return (d_pos, d_op.reshape(s_op), d_sc, d_rot, d_sh, d_sh_rest, d_extra, d_intr, d_extr, d_cc, d_ndc,
                 None, None, None, None, None, None)
 
 
 def fused_render(position, opacity, scaling, rotation, shs, intr, extr, cam_center, ndc, sh_degree, W, H, bg,
-                 with_depth=False, extra=None, nearest=0.2):
-    """(features[C,H,W], radii[P]) through the fused path; ``extr`` is the 3x4 [R|T]."""
-    return _FusedRender.apply(position, opacity, scaling, rotation, shs, extra, intr, extr, cam_center, ndc,
-                              sh_degree, W, H, bg, with_depth, nearest)
+                 with_depth=False, extra=None, nearest=0.2, features_rest=None):
+    """(features[C,H,W], radii[P]) through the fused path; ``extr`` is the 3x4 [R|T].  With ``features_rest`` the
+    inputs are the point cloud's RAW parameters (``shs`` = features[P,1,3]; see MsplatRender.render_iter_raw)."""
+    return _FusedRender.apply(position, opacity, scaling, rotation, shs, features_rest, extra, intr, extr, cam_center,
+                              ndc, sh_degree, W, H, bg, with_depth, nearest)
+
+
+class _CameraExtrinsics(torch.autograd.Function):
+    """(qrot[4], tvec[3]) -> (extrinsic[4,4], center[3]): one single-warp kernel each way (csrc/camera.cu)."""
+
+    @staticmethod
+    def forward(ctx, qrot, tvec):
+        q, t = _f32(qrot, "qrot").reshape(4), _f32(tvec, "tvec").reshape(3)
+        E = torch.empty(4, 4, dtype=torch.float32, device=q.device)
+        c = torch.empty(3, dtype=torch.float32, device=q.device)
+        with torch.cuda.device(q.device):
+            _lib.launch("pxb_camera_forward", _p(q), _p(t), _p(E), _p(c), _stream(q.device))
+        ctx.save_for_backward(q, t)
+        ctx.shapes = (qrot.shape, tvec.shape)
+        ctx.set_materialize_grads(False)
+        return E, c
+
+    @staticmethod
+    def backward(ctx, dE, dc):
+        q, t = ctx.saved_tensors
+        dE = None if dE is None else _f32(dE, "d_extrinsic")
+        dc = None if dc is None else _f32(dc, "d_center")
+        dq, dt = torch.empty_like(q), torch.empty_like(t)
+        with torch.cuda.device(q.device):
+            _lib.launch("pxb_camera_backward", _p(q), _p(t), _p(dE), _p(dc), _p(dq), _p(dt), _stream(q.device))
+        return dq.reshape(ctx.shapes[0]), dt.reshape(ctx.shapes[1])
+
+
+def camera_extrinsics(qrot: Tensor, tvec: Tensor):
+    """``CameraModel.extrinsic_matrices`` / ``camera_centers`` for one view
+    (pointrix/model/camera/camera_model.py:92-175): ``qrot[4]`` (w first; normalised inside, as the reference's
+    ``F.normalize`` does), ``tvec[3]`` -> ``(extrinsic_matrix[4,4], camera_center[3])``, differentiable."""
+    return _CameraExtrinsics.apply(qrot, tvec)
 
 
 @register_renderer
@@ -322,6 +374,29 @@ class MsplatRender(BaseObject):
             for k, c in names:
                 split[k] = feats[s:s + c]
                 s += c
+        return {"rendered_features_split": split, "uv_points": ndc, "visibility": radius > 0, "radii": radius}
+
+    def render_iter_raw(self, height, width, extrinsic_matrix, intrinsic_params, camera_center, position, opacity,
+                        scaling, rotation, features, features_rest, **kwargs) -> dict:
+        """``render_iter`` on the point cloud's RAW parameters: ``opacity`` = logits,
+        ``scaling`` = log-scales, ``rotation`` = un-normalised quaternions, ``features[P,1,3]`` /
+        ``features_rest[P,15,3]`` -- what ``GaussianPointCloud`` stores, instead of what its ``get_opacity /
+        get_scaling / get_rotation / get_shs`` properties materialise every iteration
+        (pointrix/model/point_cloud/gaussian_points.py:70-86, base_model.py:79-85).  The activations run inside
+        the fused kernels and the gradients arrive on the raw tensors.  Same returned dict as ``render_iter``."""
+        if not position.is_cuda:
+            raise RuntimeError("position must be a CUDA tensor")
+        P = position.shape[0]
+        if features.shape[0] != P or features.numel() != 3 * P or features_rest.numel() != 45 * P or self.sh_degree > 3:
+            raise ValueError("render_iter_raw needs features[P,1,3], features_rest[P,15,3] and sh_degree <= 3")
+        extr = extrinsic_matrix[:3, :]
+        intr = intrinsic_params.reshape(-1)[:4] if intrinsic_params.numel() != 4 else intrinsic_params
+        ndc = torch.zeros(P, 2, dtype=torch.float32, device=position.device, requires_grad=True)
+        ndc.retain_grad()
+        feats, radius = fused_render(position, opacity, scaling, rotation, features, intr, extr, camera_center, ndc,
+                                     self.sh_degree, width, height, self.bg_color, self.cfg.render_depth, None,
+                                     features_rest=features_rest)
+        split = {"rgb": feats[0:3], "depth": feats[3:4]} if self.cfg.render_depth else {"rgb": feats}
         return {"rendered_features_split": split, "uv_points": ndc, "visibility": radius > 0, "radii": radius}
 
     def _render_iter_ops(self, height, width, extr, intr, camera_center, position, opacity, scaling, rotation, shs,

@@ -1,0 +1,130 @@
+"""GPU parity of SURVEY.md 8f row f3: parameter activations and the camera model folded in front of the render path.
+
+* MsplatRender.render_iter_raw (raw log-scales / quaternions / logits / features + features_rest into the fused
+  kernels) against the reference's own formulation: torch's exp / F.normalize / sigmoid / cat
+  (pointrix/model/point_cloud/gaussian_points.py:70-86) feeding MsplatRender.render_iter, with autograd carrying
+  the gradients back to the raw tensors.  Tolerances: image max-abs 1e-5 (same kernels downstream; the
+  activations differ from torch's by <= 1 ulp), gradients relative 1e-3 (north star), radii equal up to the
+  rare ceil flip a 1-ulp scale difference can cause (<= 1e-5 of the Gaussians).
+* camera_extrinsics against CameraModel.extrinsic_matrices / camera_centers restated with torch ops
+  (pointrix/model/camera/camera_model.py:92-175, pointrix/utils/pose.py:40-83), values 1e-6, gradients 1e-5.
+"""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from tests.util import rel_err, scene_inputs
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def pb():
+    if not torch.cuda.is_available():
+        pytest.skip("no GPU")
+    import pointrix_b200
+
+    return pointrix_b200
+
+
+def _raw_table(sc):
+    """Raw parameters whose activations reproduce the synthetic scene (the inverse activations of
+    gaussian_points.py:29-33), with quaternions of non-unit norm."""
+    g = torch.Generator().manual_seed(9)
+    P = sc["position"].shape[0]
+    norm = (0.5 + torch.rand(P, 1, generator=g)).to(sc["rotation"].device)
+    op = sc["opacity"].clamp(1e-6, 1 - 1e-6)
+    return {"position": sc["position"].clone(), "opacity": torch.log(op / (1 - op)), "scaling": torch.log(sc["scaling"]),
+            "rotation": sc["rotation"] * norm, "features": sc["shs"][:, :1].contiguous(),
+            "features_rest": sc["shs"][:, 1:].contiguous()}
+
+
+@pytest.mark.parametrize("P,W,H,deg,depth_ch", [(20_000, 640, 360, 3, False), (20_000, 640, 360, 1, True),
+                                                (1_000_003, 1920, 1080, 3, False)])  # P not a multiple of 32 / 4
+def test_render_iter_raw_equals_torch_activations_plus_render_iter(pb, P, W, H, deg, depth_ch):
+    c, sc, cams = scene_inputs("cfg4" if P > 500_000 else "cfg1", P=P, W=W, H=H)
+    E, intr, cc = cams["extrinsic_matrix"][0], cams["intrinsic_params"], cams["camera_center"][0]
+    r = pb.parse_renderer({"name": "MsplatRender", "render_depth": depth_ch}, white_bg=True, device="cuda:0")
+    r.sh_degree = deg
+    raw = _raw_table(sc)
+    g = torch.Generator().manual_seed(2)
+    dimg = torch.randn(3 + int(depth_ch), H, W, generator=g).cuda()
+    # the reference's formulation: activations as torch ops in front of render_iter
+    a = {k: v.clone().requires_grad_() for k, v in raw.items()}
+    out_a = r.render_iter(H, W, E, intr, cc, position=a["position"], opacity=torch.sigmoid(a["opacity"]),
+                          scaling=torch.exp(a["scaling"]), rotation=F.normalize(a["rotation"]),
+                          shs=torch.cat([a["features"], a["features_rest"]], dim=1))
+    img_a = torch.cat(list(out_a["rendered_features_split"].values()), 0)
+    img_a.backward(dimg)
+    # folded
+    b = {k: v.clone().requires_grad_() for k, v in raw.items()}
+    out_b = r.render_iter_raw(H, W, E, intr, cc, **b)
+    img_b = torch.cat(list(out_b["rendered_features_split"].values()), 0)
+    img_b.backward(dimg)
+    assert list(out_b["rendered_features_split"]) == list(out_a["rendered_features_split"])
+    mism = int((out_a["radii"] != out_b["radii"]).sum())
+    assert mism <= max(1, P // 100_000), mism
+    assert torch.equal(out_a["visibility"], out_b["visibility"]) or mism > 0
+    bad = (img_a - img_b).abs() > 1e-5 * max(1.0, float(img_a.abs().max()))
+    assert float(bad.float().mean()) <= (1e-4 if mism else 0.0), float((img_a - img_b).abs().max())
+    for k in raw:
+        assert b[k].grad is not None and b[k].grad.shape == raw[k].shape, k
+        assert rel_err(b[k].grad, a[k].grad) <= 1e-3, (k, rel_err(b[k].grad, a[k].grad))
+    assert rel_err(out_b["uv_points"].grad, out_a["uv_points"].grad) <= 1e-3
+
+
+def _camera_reference(qrot, tvec):
+    """camera_model.py:92-175 + pose.py:40-83 with torch ops."""
+    q = F.normalize(qrot, dim=-1)
+    w, x, y, z = q[0], q[1], q[2], q[3]
+    R = torch.stack([torch.stack([x * x - y * y - z * z + w * w, 2 * (x * y - z * w), 2 * (x * z + y * w)]),
+                     torch.stack([2 * (x * y + z * w), -x * x + y * y - z * z + w * w, 2 * (y * z - x * w)]),
+                     torch.stack([2 * (x * z - y * w), 2 * (y * z + x * w), -x * x - y * y + z * z + w * w])])
+    Rt = torch.cat([R, tvec.reshape(3, 1)], dim=-1)
+    E = torch.cat([Rt, torch.tensor([[0.0, 0.0, 0.0, 1.0]], device=Rt.device)], dim=0)
+    return E, (-R.t() @ tvec.reshape(3, 1)).reshape(3)
+
+
+def test_camera_extrinsics_and_gradients(pb):
+    g = torch.Generator().manual_seed(4)
+    for trial in range(5):
+        q0 = (torch.randn(4, generator=g) * (0.3 + trial)).cuda()
+        t0 = torch.randn(3, generator=g).cuda()
+        qa, ta = q0.clone().requires_grad_(), t0.clone().requires_grad_()
+        qb, tb = q0.clone().requires_grad_(), t0.clone().requires_grad_()
+        Ea, ca = _camera_reference(qa, ta)
+        Eb, cb = pb.camera_extrinsics(qb, tb)
+        assert torch.allclose(Eb, Ea, atol=1e-6) and torch.allclose(cb, ca, atol=1e-5)
+        gE, gc = torch.randn(4, 4, generator=g).cuda(), torch.randn(3, generator=g).cuda()
+        ((Ea * gE).sum() + (ca * gc).sum()).backward()
+        ((Eb * gE).sum() + (cb * gc).sum()).backward()
+        assert rel_err(qb.grad, qa.grad) <= 1e-5 and rel_err(tb.grad, ta.grad) <= 1e-5
+    # only one of the two outputs used
+    qb, tb = q0.clone().requires_grad_(), t0.clone().requires_grad_()
+    qa, ta = q0.clone().requires_grad_(), t0.clone().requires_grad_()
+    pb.camera_extrinsics(qb, tb)[1].sum().backward()
+    _camera_reference(qa, ta)[1].sum().backward()
+    assert rel_err(qb.grad, qa.grad) <= 1e-5 and rel_err(tb.grad, ta.grad) <= 1e-5
+
+
+def test_camera_optimisation_path_end_to_end(pb):
+    """cfg5's call shape: (qrot, tvec) -> camera_extrinsics -> render_iter_raw -> loss -> backward reaches the camera
+    parameters and the raw Gaussian parameters in one graph."""
+    P, W, H = 20_000, 320, 240
+    c, sc, cams = scene_inputs("cfg1", P=P, W=W, H=H)
+    E0, intr = cams["extrinsic_matrix"][0], cams["intrinsic_params"]
+    # rotation matrix -> quaternion (w first) for the test input
+    R = E0[:3, :3].double().cpu()
+    w = 0.5 * torch.sqrt(torch.clamp(1 + R[0, 0] + R[1, 1] + R[2, 2], min=1e-12))
+    q = torch.tensor([w, (R[2, 1] - R[1, 2]) / (4 * w), (R[0, 2] - R[2, 0]) / (4 * w), (R[1, 0] - R[0, 1]) / (4 * w)]).float().cuda()
+    qrot, tvec = (1.7 * q).requires_grad_(), E0[:3, 3].clone().requires_grad_()
+    E, center = pb.camera_extrinsics(qrot, tvec)
+    assert torch.allclose(E, E0, atol=1e-5) and torch.allclose(center, cams["camera_center"][0], atol=1e-4)
+    r = pb.parse_renderer({"name": "MsplatRender"}, white_bg=True, device="cuda:0")
+    r.sh_degree = 3
+    raw = {k: v.requires_grad_() for k, v in _raw_table(sc).items()}
+    intr_l = intr.clone().requires_grad_()
+    out = r.render_iter_raw(H, W, E, intr_l, center, **raw)
+    out["rendered_features_split"]["rgb"].square().mean().backward()
+    for t in (qrot, tvec, intr_l, *raw.values()):
+        assert t.grad is not None and torch.isfinite(t.grad).all() and float(t.grad.abs().max()) > 0
