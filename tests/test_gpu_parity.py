@@ -304,7 +304,7 @@ def test_tight_tile_lists_render_the_same_bits_at_full_size(pb):
         radius = torch.empty(P, dtype=torch.int32, device=dev)
         tiles = torch.empty(P, dtype=torch.int32, device=dev)
         _lib.launch("pxb_fused_forward", P, 3, ops._p(sc["position"]), ops._p(sc["scaling"]), ops._p(sc["rotation"]),
-                    ops._p(sc["opacity"]), ops._p(sc["shs"]), ops._p(None), 0, 0, ops._p(intr), ops._p(extr), ops._p(cc), W, H,
+                    ops._p(sc["opacity"]), ops._p(sc["shs"]), ops._p(None), ops._p(None), 0, 0, ops._p(intr), ops._p(extr), ops._p(cc), W, H,
                     0.2, 1.3, S, tight, ops._p(rec), ops._p(depth), ops._p(radius), ops._p(tiles), stream)
         ids, tr = ops._bin(rec, S, depth, radius, tiles, W, H, tight=bool(tight))
         out = torch.empty(3, H, W, device=dev)
