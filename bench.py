@@ -355,8 +355,29 @@ def _claim_stdout():
     return real
 
 
+_WATCHDOG = {"line": None, "out": None}
+
+
+def _start_watchdog(seconds: float):
+    """A hang (a collective whose peer died, a spinning barrier) must not cost the caller its whole time limit: after
+    `seconds` the process prints the line if the headline has been measured (rank 0) and exits hard."""
+    def fire():
+        time.sleep(seconds)
+        line, out = _WATCHDOG["line"], _WATCHDOG["out"]
+        try:
+            if line is not None and out is not None and env_int("RANK", 0) == 0:
+                line.setdefault("errors", []).append(f"watchdog: not finished after {seconds:.0f} s; legs after the headline are missing")
+                print(json.dumps(line), file=out)
+                out.flush()
+        finally:
+            os._exit(0 if line is not None else 3)
+
+    threading.Thread(target=fire, daemon=True).start()
+
+
 def main():
     out_f = _claim_stdout()
+    _WATCHDOG["out"] = out_f
     try:
         _main(out_f)
     finally:
@@ -398,7 +419,9 @@ def _main(out_f):
     ap.add_argument("--no-ref-gpu", action="store_true")
     ap.add_argument("--no-loss-leg", action="store_true")
     ap.add_argument("--exchange", default="factored", choices=["factored", "allreduce", "nccl"])
+    ap.add_argument("--max-seconds", type=float, default=900.0, help="watchdog: hard exit after this many seconds")
     args = ap.parse_args()
+    _start_watchdog(args.max_seconds)
     if args.impl == "reference":
         return run_reference(args, out_f)
 
@@ -586,7 +609,10 @@ def _main(out_f):
         "gpu_launches": launches, "clocks": clocks, "untimed_settling_steps": n_pre,
     }
 
+    _WATCHDOG["line"] = line  # from here on a hang still yields the headline
+
     def finish():
+        _WATCHDOG["line"] = None
         print(json.dumps(line), file=out_f)
         out_f.flush()
 
@@ -816,9 +842,25 @@ def _rest(args, line, L):
         cnt = torch.zeros(4, dtype=torch.int64, device=dev)
         _lib.check(_lib.lib.pxb_blend_counters(ops._p(cnt)), "pxb_blend_counters")
         try:
+            # LOCAL steps only: at N > 1 this runs on rank 0 after the process group is gone, so the step here is
+            # render -> loss -> backward WITHOUT the exchange (the peers have left: an exchange would wait for them
+            # forever -- it did, once) and with the gradient sink detached.  The blend kernels do not depend on it.
+            from pointrix_b200 import renderer as _rmod
+
+            _rmod.set_grad_sink(None)
             n = min(K, V)
             for s in range(n):
-                step_fn(W_ + s)
+                v = view_of(W_ + s)
+                E, I, Cc = camera(cams_d, v)
+                if train:
+                    for p_ in params.values():
+                        p_.grad = None
+                    o_ = r.render_iter(H, W, E, I, Cc, **params)
+                    PL.l1_ssim_loss(o_["rendered_features_split"]["rgb"].unsqueeze(0), targets[v % NT].unsqueeze(0),
+                                    LAMBDA_SSIM)["loss"].backward(loss_w)
+                else:
+                    with torch.no_grad():
+                        r.render_iter(H, W, E, I, Cc, **params, **extra_kw)
             torch.cuda.synchronize()
         finally:
             _lib.check(_lib.lib.pxb_blend_counters(None), "pxb_blend_counters")

@@ -101,11 +101,14 @@ def test_argument_errors_are_return_codes():
     assert L.pxb_sh_grad_gather(arr, 0, 0, 2, 10, 3, one, C.c_void_p(20), null) == -4                  # d_shs misaligned
     assert L.pxb_p2p_allreduce(arr, 6, 0, 0, 2, null) == -4                                            # n_f32 % (4*world)
     assert L.pxb_nvls_allreduce(null, 8, 0, 0, 2, null) == -1
-    assert L.pxb_render_forward(0, 3, *([null] * 6), 0, 0, null, null, null, 8, 8, 0.2, 1.3, 1.0, 12, 100,
+    assert L.pxb_render_forward(0, 3, *([null] * 7), 0, 0, null, null, null, 8, 8, 0.2, 1.3, 1.0, 12, 100,
                                 *([null] * 10), 0, null, null) == -1                                   # P = 0
-    assert L.pxb_fused_backward(10, 5, *([one] * 4), 0, 0, one, one, one, 8, 8, 12, *([one] * 13), null) == -2  # SH degree
-    assert L.pxb_fused_backward(10, 3, *([one] * 4), 0, 0, one, one, one, 8, 8, 12, one, one, one, one, one, one, one,
-                                null, null, one, one, one, null) == -1                                 # neither d_shs nor d_rgb
+    assert L.pxb_fused_backward(10, 5, *([one] * 4), null, null, 0, 0, one, one, one, 8, 8, 12, *([one] * 14), null) == -2  # SH degree
+    assert L.pxb_fused_backward(10, 3, *([one] * 4), null, null, 0, 0, one, one, one, 8, 8, 12, one, one, one, one, one, one, one,
+                                null, null, null, one, one, one, null) == -1                           # neither d_shs nor d_rgb
+    assert L.pxb_fused_backward(10, 3, *([one] * 3), null, one, one, 0, 0, one, one, one, 8, 8, 12, one, one, one, one, one, one, one,
+                                one, one, null, one, one, one, null) == -1                             # raw mode without the logits
+    assert L.pxb_camera_forward(null, one, one, one, null) == -1
     assert [L.pxb_loss_workspace_bytes(0, 3, 8, 8), L.pxb_loss_workspace_bytes(1, 1, 1, 1)] == [0, 8]
     grp = (_lib.AdamGroup * 1)(_lib.AdamGroup(16, 16, 16, 16, 10, 3, 3, 0, 2, 0, 1, 1e-3))        # grad_stride < offset + width
     assert L.pxb_adam_densify_step(C.cast(grp, C.c_void_p), 1, 0.9, 0.999, 1e-15, 0, null, null, 1.0, 1.0, null, null, null, null) == -1

@@ -1,5 +1,6 @@
 """The driver's own command, end to end: `python bench.py --gpus 1` must exit 0 and print ONE JSON line that
-carries every object the contract names (round 1 lost its headline to an un-guarded side leg)."""
+carries every object the contract names (round 1 lost its headline to an un-guarded side leg).
+(Named test_zz_*: the longest tests of the suite run last.)"""
 import json
 import os
 import subprocess
