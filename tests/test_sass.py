@@ -66,16 +66,57 @@ def test_blend_loops_use_wide_shared_loads_and_mufu():
 
 
 def test_hot_kernels_do_not_spill():
+    """No local memory in any hot kernel, and no stack either except 24 bytes in two places: the 4-CTA/SM build of the
+    C <= 4 blend backward (it trades them for the fourth resident CTA: measured faster than the spill-free
+    80-register build) and the 16-pairs-per-thread scatter of the N-level tile sort (3 CTAs/SM)."""
     res = subprocess.run([_cuobjdump(), "-res-usage", os.path.join(ROOT, "pointrix_b200", "libpointrix_b200.so")],
                          capture_output=True, text=True, check=True).stdout
     hot = (r"blend_fwd_kernelILi3ELi12E", r"blend_bwd_kernelILi3ELi12E", r"fused_fwd_kernelILi16E", r"fused_bwd_kernelILi16E",
-           r"l1_ssim_fwd_kernel", r"l1_ssim_bwd_kernel", r"rs_scatter_kernel", r"emit_keys_kernel")
+           r"l1_ssim_fwd_kernel", r"l1_ssim_bwd_kernel", r"rs_scatter_kernel", r"emit_keys_kernel", r"adam_densify_kernel",
+           r"compact_kernel")
     seen = 0
     blocks = re.findall(r"Function (\S+?):\s*\n\s*(.*)", res)
     for name, usage in blocks:
         if any(re.search(h, name) for h in hot):
             seen += 1
             local = int(re.search(r"LOCAL:(\d+)", usage).group(1))
+            stack = int(re.search(r"STACK:(\d+)", usage).group(1))
             regs = int(re.search(r"REG:(\d+)", usage).group(1))
             assert local == 0 and regs <= 128, (name, usage)
-    assert seen >= 8
+            some = re.search(r"blend_bwd_kernelILi\dELi\d+ELi4E|rs_scatter_kernelILi\dELi16E", name)
+            assert stack <= (24 if some else 0), (name, usage)
+    assert seen >= 10
+
+
+def test_every_kernel_of_the_step_waits_on_its_programmatic_dependency():
+    """PDL: each kernel of the render / loss / optimizer chain starts with griddepcontrol.wait (SASS: ACQBULK), which is
+    what allows launch_k() to set programmatic stream serialization on it (common.cuh)."""
+    chain = (r"fused_fwd_kernel", r"compact_kernel", r"count_visible_kernel", r"rs_tile_scan_kernel", r"rs_scatter_kernel",
+             r"rs_tile_hist_kernel", r"emit_keys_kernel", r"tile_range_kernel", r"blend_fwd_kernel", r"blend_bwd_kernel",
+             r"fused_bwd_kernel", r"l1_ssim_fwd_kernel", r"l1_ssim_bwd_kernel", r"loss_finalize_fused_kernel",
+             r"adam_densify_kernel", r"camera_fwd_kernel", r"camera_bwd_kernel")
+    for pat in chain:
+        for k, sass in _kernels(pat).items():
+            assert "ACQBULK" in sass, k
+
+
+def test_depth_sort_epilogues_aggregate_their_atomics_in_the_warp():
+    """The scatter passes that bump their successor's counters (histogram of the next digit / chunk tile sums) find the
+    lanes hitting the same word with MATCH.ANY and issue ONE RED per group (binning.cu)."""
+    for pat in (r"rs_scatter_kernelILi8ELi8ELi1E", r"rs_scatter_kernelILi8ELi8ELi2E"):
+        for k, sass in _kernels(pat).items():
+            assert "MATCH.ANY" in sass and "REDG.E.ADD" in sass, k
+    for k, sass in _kernels(r"rs_scatter_kernelILi8ELi8ELi2E").items():
+        assert "REDUX.SUM" in sass, k   # __reduce_add_sync of the group's tile counts
+    for k, sass in _kernels(r"rs_scatter_kernelILi7ELi16ELi0E").items():
+        assert "MATCH.ANY" not in sass and "REDG" not in sass, k   # the N-level tile sort keeps separate histograms
+
+
+def test_bulk_copy_staging_variant_is_what_it_says():
+    """The measured alternative of the forward blend (PXB_BLEND_STAGING=bulk): cp.async.bulk + mbarrier.  In SASS the
+    bulk copy is UBLKCP -- an instruction of the UNIFORM datapath: one copy per issue, the warp loops over its lanes --
+    which is why 256 per-record copies lose to LDG.128 + STS.128 by all threads."""
+    for k, sass in _kernels(r"blend_fwd_kernelILi3ELi12ELb1E").items():
+        assert "UBLKCP" in sass and "SYNCS" in sass, k
+    for k, sass in _kernels(r"blend_fwd_kernelILi3ELi12ELb0E").items():
+        assert "UBLKCP" not in sass, k
