@@ -821,12 +821,14 @@ def _rest(args, line, L):
     dom = max(render_kernels.items(), key=lambda kv: kv[1]["ms_total"])[0]
     dom_ms = dom_timed["ms_avg"] if (dom == DOMINANT and dom_timed) else kern[dom]["ms_avg"]
     dom_gbs = alg[dom] / (dom_ms * 1e-3) / 1e9
-    traffic = None  # DRAM bytes per launch of that kernel from the committed ncu --set full capture
+    traffic, traffic_src = None, None  # DRAM bytes per launch of that kernel from the committed ncu --set full capture
     tj = os.path.join(ROOT, "profiles", "ncu_traffic.json")
-    if cfg == "cfg4" and os.path.exists(tj):
-        traffic = json.load(open(tj)).get(dom, {}).get("dram_bytes_per_launch")
+    if cfg == "cfg4" and train and os.path.exists(tj):
+        ent = json.load(open(tj)).get(dom, {})
+        traffic = ent.get("dram_bytes_per_launch")
+        traffic_src = "profiles/ncu_traffic.json: " + ent.get("source", "?") + ("; " + ent["note"] if "note" in ent else "")
     line["roofline"] = {"kernel": dom, "bound": "hbm", "achieved": round(dom_gbs, 1), "peak": hbm_peak, "unit": "GB/s",
-                        "frac": round(dom_gbs / hbm_peak, 4), "traffic": traffic, "peak_source": peak_src,
+                        "frac": round(dom_gbs / hbm_peak, 4), "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                         "alg_bytes_per_launch": int(alg[dom]),
                         "ms_avg_in_timed_region": round(dom_ms, 4), "share_of_step": round(dom_ms * K / ms, 4),
                         "limiter": "issue",
