@@ -13,6 +13,7 @@ reference's ~14 kernels + ~40 torch ops; the autograd graph of ``render_iter``
 """
 from __future__ import annotations
 
+import collections
 import ctypes as C
 import time
 from dataclasses import dataclass
@@ -84,6 +85,49 @@ def _count_word(dev_index: int):
         t = torch.zeros(16, dtype=torch.int32).pin_memory()
         w = _COUNT_WORD[dev_index] = (t, C.c_int.from_address(t.data_ptr()))
     return w
+
+
+# ---- sync-free forward (inference) ---------------------------------------------------------------------------------
+# Normally every forward spins on the pinned word until the key emission has stored the intersection count: a view
+# that overflows the learnt capacity is re-binned before anyone sees its image (exactness), at the price of one
+# host <-> device rendezvous per view.  With MsplatRender.Config.sync_free (and only under torch.no_grad()) the check
+# TRAILS: the call returns at once, the count lands in one of 15 pinned slots, and the next call (or
+# check_sync_free()) reads it -- raising if that earlier image was truncated, after raising the capacity.  Nothing
+# in the forward then waits on the device, which is what CUDA-graph capture needs (the GUI's render loop,
+# pointrix/webgui/gui.py:160-209).
+_SYNC_FREE = False
+_PENDING: Dict[int, "collections.deque"] = {}
+_NEXT_SLOT: Dict[int, int] = {}
+
+
+def _slot_word(dev_index: int, slot: int):
+    t, _ = _count_word(dev_index)
+    return C.c_int.from_address(t.data_ptr() + 4 * slot)
+
+
+def _check_pending(dev_index: int, block: bool) -> None:
+    dq = _PENDING.get(dev_index)
+    while dq:
+        slot, cap, ckey = dq[0]
+        w = _slot_word(dev_index, slot)
+        n = w.value
+        if n == -1:
+            if not block:
+                return
+            n = _wait_count(w)
+        dq.popleft()
+        ops.LAST_N[(dev_index, True)] = n
+        if n > cap:
+            _CAPACITY[ckey] = int(n * 1.25) + 65536
+            raise RuntimeError(f"pointrix_b200: a sync-free render binned {n} tile intersections into a capacity of {cap}: "
+                               "that image was truncated.  The capacity has been raised; render the view again")
+
+
+def check_sync_free(device=None) -> None:
+    """Wait for the intersection counts of all sync-free renders still in flight on ``device`` (default: the current
+    one) and raise if any of them overflowed its capacity."""
+    idx = torch.cuda.current_device() if device is None else torch.device(device).index
+    _check_pending(idx, block=True)
 
 
 def _wait_count(word) -> int:
@@ -173,17 +217,27 @@ class _FusedRender(torch.autograd.Function):
                 ws = _WORKSPACE[wkey] = E((lib.pxb_render_workspace_bytes(P, cap, W, H),), dtype=torch.uint8, device=dev)
             idx_sorted = E((cap,), dtype=i32, device=dev)
             evs, ev_arr = _stage_events(timer, _FWD_STAGES)
+            sync_free = _SYNC_FREE and not torch.is_grad_enabled()
+            slot = 0
+            if sync_free:  # trailing check: earlier calls first, then a pinned slot of this call's own
+                dq = _PENDING.setdefault(dev.index, collections.deque())
+                _check_pending(dev.index, block=len(dq) >= 14)
+                slot = _NEXT_SLOT[dev.index] = _NEXT_SLOT.get(dev.index, 0) % 15 + 1
+                word = _slot_word(dev.index, slot)
             word.value = -1
             args = (P, int(sh_degree), _p(pos), _p(sc), _p(rot), _p(op), _p(sh), _p(sh_r), _p(ex), n_extra, int(with_depth),
                     _p(intr_c), _p(extr_c), _p(cc), W, H, float(nearest), 1.3, float(bg), S, cap, _p(rec), _p(depth),
                     _p(radius), _p(idx_sorted), _p(tile_range), _p(final_T), _p(ncontrib), _p(out),
-                    host_t.data_ptr(), _p(ws), ws.numel(), ev_arr, stream)
+                    host_t.data_ptr() + 4 * slot, _p(ws), ws.numel(), ev_arr, stream)
             if same_dev:
                 _lib.check(lib.pxb_render_forward(*args), "pxb_render_forward")
             else:
                 with torch.cuda.device(dev):
                     _lib.check(lib.pxb_render_forward(*args), "pxb_render_forward")
             _lib.count_launches("pxb_render_forward", W, H)
+            if sync_free:
+                _PENDING[dev.index].append((slot, cap, ckey))
+                break
             n = _wait_count(word)
             ops.LAST_N[(dev.index, True)] = n
             if evs is not None:
@@ -320,6 +374,7 @@ class MsplatRender(BaseObject):
         update_sh_iter: int = 1000
         max_sh_degree: int = 3
         render_depth: bool = False
+        sync_free: bool = False  # not in the reference: no host wait in no_grad forwards (see check_sync_free)
 
     cfg: Config
 
@@ -361,8 +416,13 @@ class MsplatRender(BaseObject):
         fused_ok = (shs.dim() == 3 and shs.shape[1] == 16 and shs.shape[2] == 3 and self.sh_degree <= 3
                     and n_ch <= ops.MAX_CH and P > 0)
         if fused_ok:
-            feats, radius = fused_render(position, opacity, scaling, rotation, shs, intr, extr, camera_center, ndc,
-                                         self.sh_degree, width, height, self.bg_color, self.cfg.render_depth, extra)
+            global _SYNC_FREE
+            _SYNC_FREE = bool(getattr(self.cfg, "sync_free", False))
+            try:
+                feats, radius = fused_render(position, opacity, scaling, rotation, shs, intr, extr, camera_center, ndc,
+                                             self.sh_degree, width, height, self.bg_color, self.cfg.render_depth, extra)
+            finally:
+                _SYNC_FREE = False
         else:
             feats, radius = self._render_iter_ops(height, width, extr, intr, camera_center, position, opacity, scaling,
                                                   rotation, shs, extra, ndc)
