@@ -279,8 +279,11 @@ class ShFactoredExchange:
         h.barrier(channel=0)  # every rank's replica (gradients, d_rgb, camera centre) is written
         self._ev0.record(main)
         self._side.wait_event(self._ev0)
-        lib.launch("pxb_sh_grad_gather", self._peer_arrays[cur], self.rgb_off, self.cam_off, self.world, self.P,
-                   sh_degree, C.c_void_p(pos.data_ptr()), C.c_void_p(d_sh.data_ptr()), C.c_void_p(self._side.cuda_stream))
+        # the side stream is made current around the launch so that a stage timer's events (recorded on the current
+        # stream by _lib.launch) bracket the kernel where it runs -- on the main stream they measured nothing
+        with torch.cuda.stream(self._side):
+            lib.launch("pxb_sh_grad_gather", self._peer_arrays[cur], self.rgb_off, self.cam_off, self.world, self.P,
+                       sh_degree, C.c_void_p(pos.data_ptr()), C.c_void_p(d_sh.data_ptr()), C.c_void_p(self._side.cuda_stream))
         self._ev1.record(self._side)
         if self._nvls:
             lib.launch("pxb_nvls_allreduce", C.c_void_p(h.multicast_ptr), self.n_f32, self.n_i32, self.rank, self.world,
