@@ -34,6 +34,13 @@ Two sources, both the reference itself:
       of the config / pose / base-object modules stubbed) and calls DensificationController.preprocess --
       accumulate_viewspace_grad + the masked updates of grad_accum / acc_steps / max_radii -- three iterations
       on seeded inputs (two views per iteration) -> tests/golden/ref_controller.npz.
+
+  python oracle/make_golden.py --from-ref-densify
+      (this container, CPU) the clone / split / prune / opacity-reset surgery: the reference's OWN GaussianPointCloud
+      (points.py, gaussian_points.py, point_utils.py), pose.py and DensificationController.densify (gs.py, base.py)
+      executed where they lie on a 3000-point cloud with a populated torch.optim.Adam, at steps 600 (clone + split +
+      prune), 3000 (... + opacity reset) and 3100 (prune with the size thresholds) -> tests/golden/ref_densify.npz:
+      the table, both Adam moments and the controller state before and after each call.
 """
 from __future__ import annotations
 
@@ -389,8 +396,130 @@ def from_ref_controller(out_path):
     print("wrote", out_path)
 
 
+def from_ref_densify(out_path):
+    """Golden vectors of DensificationController.densify (pointrix/controller/gs.py:72-234, 286-313, 336-341;
+    base.py:89-96) with the real point-cloud surgery (points.py:179-357, point_utils.py:51-106)."""
+    import importlib.util
+    import types
+    from dataclasses import fields
+
+    import numpy as np
+    import torch
+
+    ref = "/root/reference/pointrix"
+
+    def mod(name, **attrs):
+        m = types.ModuleType(name)
+        m.__path__ = []
+        for k, v in attrs.items():
+            setattr(m, k, v)
+        sys.modules[name] = m
+        return m
+
+    def load(name, path):
+        spec = importlib.util.spec_from_file_location(name, path)
+        m = importlib.util.module_from_spec(spec)
+        sys.modules[name] = m
+        spec.loader.exec_module(m)
+        return m
+
+    class BaseObject:  # pointrix/utils/base.py:24-39 without omegaconf
+        def __init__(self, cfg=None, *args, **kwargs):
+            super().__init__()
+            known = {f.name for f in fields(self.Config)}
+            self.cfg = self.Config(**{k: v for k, v in (cfg or {}).items() if k in known})
+            self.setup(*args, **kwargs)
+
+        def setup(self, *args, **kwargs):
+            pass
+
+    class BaseModule(BaseObject, torch.nn.Module):
+        pass
+
+    for name in ("pointrix", "pointrix.utils", "pointrix.controller", "pointrix.model", "pointrix.model.utils",
+                 "pointrix.model.point_cloud", "pointrix.model.point_cloud.utils", "pointrix.logger"):
+        mod(name)
+    mod("pointrix.utils.config", C=lambda *a, **k: None)
+    mod("pointrix.utils.base", BaseObject=BaseObject, BaseModule=BaseModule)
+    mod("pointrix.logger.writer", Logger=types.SimpleNamespace(log=lambda *a, **k: None))
+    mod("plyfile", PlyData=None, PlyElement=None)  # the un-vendored PLY codec: not touched by the surgery
+    load("pointrix.utils.registry", os.path.join(ref, "utils", "registry.py"))
+    pose = load("pointrix.utils.pose", os.path.join(ref, "utils", "pose.py"))
+    pu = load("pointrix.model.point_cloud.utils.point_utils", os.path.join(ref, "model", "point_cloud", "utils", "point_utils.py"))
+    mod("pointrix.model.utils.gaussian_utils", sigmoid_inv=pu.sigmoid_inv)
+    load("pointrix.model.point_cloud.points", os.path.join(ref, "model", "point_cloud", "points.py"))
+    gp = load("pointrix.model.point_cloud.gaussian_points", os.path.join(ref, "model", "point_cloud", "gaussian_points.py"))
+    load("pointrix.controller.base", os.path.join(ref, "controller", "base.py"))
+    gs = load("pointrix.controller.gs", os.path.join(ref, "controller", "gs.py"))
+
+    # the split samples with torch.zeros(..., device="cuda") (gs.py:166): this container has no GPU
+    zeros = torch.zeros
+    torch.zeros = lambda *a, **k: zeros(*a, **{kk: ("cpu" if kk == "device" and str(vv).startswith("cuda") else vv) for kk, vv in k.items()})
+
+    np.random.seed(0)
+    torch.manual_seed(0)
+    P0 = 3000
+    init = types.SimpleNamespace(init_type="random", num_points=P0, radius=1.0, feat_dim=3)
+    pc = gp.GaussianPointCloud({"initializer": init, "max_sh_degree": 3})
+    names = ("position", "features", "features_rest", "scaling", "rotation", "opacity")
+    g = torch.Generator().manual_seed(1)
+    with torch.no_grad():  # a trained-looking table: spread scales, opacities on both sides of the pruning threshold
+        pc.scaling.add_(torch.randn(P0, 3, generator=g) * 0.8)
+        pc.rotation.copy_(torch.randn(P0, 4, generator=g))
+        pc.opacity.copy_(torch.randn(P0, 1, generator=g) * 3.0 - 1.0)
+        pc.features_rest.copy_(torch.randn(P0, 15, 3, generator=g) * 0.1)
+    lrs = {"position": 0.00016, "features": 0.0025, "features_rest": 0.000125, "scaling": 0.005, "rotation": 0.001, "opacity": 0.05}
+    opt = torch.optim.Adam([{"params": [getattr(pc, n)], "lr": lrs[n], "name": "point_cloud." + n} for n in names], eps=1e-15)
+    for _ in range(3):  # populate the Adam state
+        for n in names:
+            getattr(pc, n).grad = torch.randn(getattr(pc, n).shape, generator=g) * 1e-3
+        opt.step()
+
+    ctl = object.__new__(gs.DensificationController)
+    ctl.cfg = types.SimpleNamespace(normalize_grad=True, max_points=5000000, densify_stop_iter=15000, densify_start_iter=500)
+    ctl.device, ctl.point_cloud, ctl.optimizer, ctl.cameras_extent = "cpu", pc, opt, 2.5
+    ctl.split_num, ctl.min_opacity, ctl.prune_interval, ctl.densify_grad_threshold = 2, 0.005, 100, 0.0002
+    ctl.duplicate_interval, ctl.opacity_reset_interval, ctl.percent_dense = 100, 3000, 0.01
+    ctl.width, ctl.height = 640, 360
+
+    def snapshot(tag, out):
+        for n in names:
+            p_ = getattr(pc, n)
+            out[f"{tag}_{n}"] = p_.detach().clone().numpy()
+            st = opt.state[p_]
+            out[f"{tag}_{n}_exp_avg"] = st["exp_avg"].clone().numpy()
+            out[f"{tag}_{n}_exp_avg_sq"] = st["exp_avg_sq"].clone().numpy()
+            out[f"{tag}_{n}_step"] = np.float64(float(st["step"]))
+        out[f"{tag}_grad_accum"] = ctl.grad_accum.clone().numpy()
+        out[f"{tag}_acc_steps"] = ctl.acc_steps.clone().numpy()
+        out[f"{tag}_max_radii"] = ctl.max_radii.clone().numpy()
+
+    out = {"cameras_extent": np.float64(ctl.cameras_extent)}
+    for case, step in enumerate((600, 3000, 3100)):
+        n_pts = len(pc)
+        ctl.step = step
+        ctl.grad_accum = torch.rand(n_pts, 1, generator=g) * 6e-4          # average gradients around the 2e-4 threshold
+        ctl.acc_steps = torch.randint(0, 4, (n_pts, 1), generator=g).float()  # zeros: 0/0 -> nan -> 0 in densify()
+        ctl.max_radii = torch.rand(n_pts, generator=g) * 30.0
+        snapshot(f"c{case}_before", out)
+        out[f"c{case}_step"] = np.int64(step)
+        torch.manual_seed(100 + case)                                     # the split's torch.normal draws from here
+        orig_empty = torch.cuda.empty_cache
+        torch.cuda.empty_cache = lambda: None
+        try:
+            ctl.densify()
+        finally:
+            torch.cuda.empty_cache = orig_empty
+        snapshot(f"c{case}_after", out)
+    torch.zeros = zeros
+    np.savez_compressed(out_path, **out)
+    print("wrote", out_path, {k: v.shape for k, v in out.items() if k.endswith("after_position")})
+
+
 if __name__ == "__main__":
-    if "--from-ref-controller" in sys.argv:
+    if "--from-ref-densify" in sys.argv:
+        from_ref_densify(os.path.join(ROOT, "tests", "golden", "ref_densify.npz"))
+    elif "--from-ref-controller" in sys.argv:
         from_ref_controller(os.path.join(ROOT, "tests", "golden", "ref_controller.npz"))
     elif "--from-ref-plugin" in sys.argv:
         from_ref_plugin(os.path.join(ROOT, "tests", "golden", "ref_plugin.npz"))

@@ -13,6 +13,7 @@ from .ops import (  # noqa: F401
     rasterization,
     sort_gaussian,
 )
+from . import densify  # noqa: F401  (clone / split / prune / opacity reset, pointrix/controller/gs.py)
 from . import io  # noqa: F401  (.ply / .pth formats of the Gaussian table, pointrix/model/point_cloud/points.py:359-427)
 from . import loss  # noqa: F401  (l1_loss / l2_loss / psnr / ssim / l1_ssim_loss, pointrix/model/loss.py)
 from . import optim  # noqa: F401  (fused Adam + densification statistics, pointrix/optimizer/optimizer.py, controller/gs.py)
@@ -21,5 +22,5 @@ from .renderer import MsplatRender, RenderFeatures, camera_extrinsics, fused_ren
 
 __all__ = [
     "project_point", "compute_cov3d", "ewa_project", "sort_gaussian", "compute_sh", "alpha_blending",
-    "rasterization", "MsplatRender", "RenderFeatures", "RENDERER_REGISTRY", "parse_renderer", "fused_render", "camera_extrinsics", "loss", "io", "optim",
+    "rasterization", "MsplatRender", "RenderFeatures", "RENDERER_REGISTRY", "parse_renderer", "fused_render", "camera_extrinsics", "loss", "io", "optim", "densify",
 ]

@@ -260,3 +260,43 @@ def test_plugin_host_logic_matches_reference_plugin_golden():
         degs.append(r.sh_degree)
     assert degs == z["sh_schedule"].tolist()
     assert r.bg_color == float(z["bg_black"])
+
+
+def test_densification_surgery_matches_reference_controller_golden():
+    """pointrix_b200.densify.DensificationController (clone / split / prune / opacity reset + Adam-state surgery) against
+    tests/golden/ref_densify.npz: the reference's OWN GaussianPointCloud + DensificationController.densify executed
+    where they lie on a populated torch.optim.Adam (oracle/make_golden.py --from-ref-densify), three schedule points."""
+    import types
+
+    import numpy as np
+
+    from pointrix_b200 import densify, optim
+
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_densify.npz"))
+    names = ("position", "features", "features_rest", "scaling", "rotation", "opacity")
+    for case in range(3):
+        pre, post = f"c{case}_before", f"c{case}_after"
+        t = lambda k: torch.from_numpy(z[k])  # noqa: E731
+        opt = types.SimpleNamespace(
+            params={n: t(f"{pre}_{n}").clone().requires_grad_() for n in names},
+            state={n: {"exp_avg": t(f"{pre}_{n}_exp_avg").clone(), "exp_avg_sq": t(f"{pre}_{n}_exp_avg_sq").clone()} for n in names})
+        P = opt.params["position"].shape[0]
+        stats = optim.DensificationStats(P, "cpu", 640, 360)
+        stats.grad_accum, stats.acc_steps, stats.max_radii = t(f"{pre}_grad_accum").clone(), t(f"{pre}_acc_steps").clone(), t(f"{pre}_max_radii").clone()
+        ctl = densify.DensificationController(opt, stats, densify.DensifyConfig(), cameras_extent=float(z["cameras_extent"]))
+        ctl.step = int(z[f"c{case}_step"])
+        torch.manual_seed(100 + case)  # the generator's seed for this case: the split's torch.normal draws from it
+        ctl.densify()
+        assert len(ctl) == z[f"{post}_position"].shape[0] != P, case
+        for n in names:
+            assert torch.allclose(opt.params[n].detach(), t(f"{post}_{n}"), rtol=1e-6, atol=1e-7), (case, n)
+            assert opt.params[n].requires_grad and opt.params[n].is_leaf
+            for key in ("exp_avg", "exp_avg_sq"):
+                assert torch.equal(opt.state[n][key], t(f"{post}_{n}_{key}")), (case, n, key)
+        assert torch.equal(stats.grad_accum, t(f"{post}_grad_accum")) and torch.equal(stats.acc_steps, t(f"{post}_acc_steps"))
+        assert torch.equal(stats.max_radii, t(f"{post}_max_radii"))
+    # schedule: nothing happens before densify_start_iter or off the intervals; the step counter advances
+    ctl.step = 10
+    assert ctl.f_step() is False and ctl.step == 11
+    ctl.step = 601
+    assert ctl.f_step() is False
