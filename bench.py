@@ -420,6 +420,9 @@ def _main(out_f):
     ap.add_argument("--no-loss-leg", action="store_true")
     ap.add_argument("--exchange", default="factored", choices=["factored", "allreduce", "nccl"])
     ap.add_argument("--max-seconds", type=float, default=900.0, help="watchdog: hard exit after this many seconds")
+    ap.add_argument("--train-loop", type=int, default=0,
+                    help="N = 1 side leg: run this many iterations of the full training loop (raw parameters, fused Adam + "
+                         "statistics, densification) of the config and report it")
     args = ap.parse_args()
     _start_watchdog(args.max_seconds)
     if args.impl == "reference":
@@ -884,9 +887,61 @@ def _rest(args, line, L):
         line["ref_gpu"] = guarded(ref_gpu_run, cfg, mode, min(K, 10), dev)
     if world == 1 and train and not args.no_loss_leg:
         line["photometric_loss"] = guarded(photometric_loss_leg, H, W, K, dev)
+    if world == 1 and train and args.train_loop > 0:
+        line["training_loop"] = guarded(training_loop_leg, cfg, args.train_loop, dev)
     if world == 1 and not args.no_cpu_baseline:  # rank 0 at N = 1 only
         # bounded sample (tens of seconds of CPU work): the full cloud, every 8th tile blended, scaled by intersections
         line["cpu_baseline"] = guarded(cpu_tile_sample_estimate, cfg, mode, 8)
+
+
+def training_loop_leg(cfg_name, iters, dev):
+    """BASELINE config 2's call shape, every piece from this repo: the 3DGS training loop on the point cloud's RAW
+    parameters -- camera_extrinsics -> render_iter_raw -> fused L1/SSIM loss -> backward -> GaussianAdam.step with
+    the densification statistics in the same launch -> DensificationController.f_step (clone / split / prune /
+    opacity reset on nerf.yaml's schedule) -> SH degree warm-up.  `--train-loop N` runs N iterations (the full
+    schedule is 30 000; a few thousand are enough to cross the first densifications at 600, 700, ...) and reports
+    iterations/s including everything, plus the table size it ends with."""
+    import torch
+
+    import pointrix_b200 as pb
+    from pointrix_b200 import densify, optim, scene
+    from pointrix_b200 import loss as PL
+
+    c, sc, cams = scene.make_config(cfg_name)
+    H, W, V = c["H"], c["W"], c["views"]
+    op = sc["opacity"].clamp(1e-6, 1 - 1e-6)
+    table = {"position": sc["position"], "features": sc["shs"][:, :1].contiguous(), "features_rest": sc["shs"][:, 1:].contiguous(),
+             "scaling": torch.log(sc["scaling"]), "rotation": sc["rotation"], "opacity": torch.log(op / (1 - op))}
+    params = {k: v.to(dev).contiguous().requires_grad_() for k, v in table.items()}
+    cams = {k: v.to(dev) for k, v in cams.items()}
+    targets = scene.target_images(min(V, 8), H, W).to(dev)
+    r = pb.parse_renderer({"name": "MsplatRender"}, white_bg=True, device=str(dev))
+    opt = optim.GaussianAdam(params)
+    stats = optim.DensificationStats(c["P"], dev, W, H)
+    ctl = densify.DensificationController(opt, stats, cameras_extent=4.03)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    n_changed = 0
+    for it in range(iters):
+        r.update_sh_degree(it)
+        v = it % V
+        p = opt.params
+        out = r.render_iter_raw(H, W, cams["extrinsic_matrix"][v], cams["intrinsic_params"], cams["camera_center"][v],
+                                p["position"], p["opacity"], p["scaling"], p["rotation"], p["features"], p["features_rest"])
+        PL.l1_ssim_loss(out["rendered_features_split"]["rgb"].unsqueeze(0), targets[v % targets.shape[0]].unsqueeze(0),
+                        LAMBDA_SSIM)["loss"].backward()
+        if ctl.wants_statistics():
+            opt.update_model(stats=stats, uv_points=out["uv_points"], radii=out["radii"])
+        else:
+            opt.update_model()
+        n_changed += int(ctl.f_step())
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    return {"iterations": iters, "it_per_s": round(iters / (ms / 1e3), 2), "ms_per_iteration": round(ms / iters, 4),
+            "points_start": c["P"], "points_end": len(ctl), "densification_events": n_changed, "sh_degree_end": r.sh_degree,
+            "note": "render_iter_raw + fused loss + backward + fused Adam/statistics + densification controller, one view per iteration"}
 
 
 def photometric_loss_leg(H, W, K, dev):
