@@ -38,7 +38,7 @@ Two sources, both the reference itself:
   python oracle/make_golden.py --from-ref-densify
       (this container, CPU) the clone / split / prune / opacity-reset surgery: the reference's OWN GaussianPointCloud
       (points.py, gaussian_points.py, point_utils.py), pose.py and DensificationController.densify (gs.py, base.py)
-      executed where they lie on a 3000-point cloud with a populated torch.optim.Adam, at steps 600 (clone + split +
+      executed where they lie on an 800-point cloud with a populated torch.optim.Adam, at steps 600 (clone + split +
       prune), 3000 (... + opacity reset) and 3100 (prune with the size thresholds) -> tests/golden/ref_densify.npz:
       the table, both Adam moments and the controller state before and after each call.
 """
@@ -458,7 +458,7 @@ def from_ref_densify(out_path):
 
     np.random.seed(0)
     torch.manual_seed(0)
-    P0 = 3000
+    P0 = 800
     init = types.SimpleNamespace(init_type="random", num_points=P0, radius=1.0, feat_dim=3)
     pc = gp.GaussianPointCloud({"initializer": init, "max_sh_degree": 3})
     names = ("position", "features", "features_rest", "scaling", "rotation", "opacity")

@@ -67,3 +67,34 @@ def test_reference_arm_never_maps_the_product_library():
             "assert 'pointrix_b200' not in sys.modules") % ROOT
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stderr[-2000:]
+
+
+def test_product_arm_fails_loudly_without_a_gpu():
+    """No CPU fallback: on a box without CUDA the product arm of bench.py must stop with a clear message, not run the
+    oracle in its place."""
+    import torch
+
+    if torch.cuda.is_available():
+        import pytest
+
+        pytest.skip("this box has a GPU")
+    env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")}
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1", "--warmup", "1"], capture_output=True,
+                         text=True, env=env, timeout=300)
+    assert out.returncode != 0 and out.stdout.strip() == ""
+    assert "needs a GPU (no CPU fallback)" in out.stderr
+
+
+def test_algorithmic_bytes_follow_the_survey_formulas():
+    """blend forward (28 + 4C) B/isect + 4 (C+2) HW; blend backward the same gather + (4C + 8) HW + 8 (6+C)
+    B/isect of ideal atomics; the factored exchange drops the 192-byte SH gradient write of the per-Gaussian backward."""
+    import bench
+
+    P, N, H, W, C, S, tiles = 1_000_000, 7_600_000, 1080, 1920, 3, 12, 8160
+    a = bench.algorithmic_bytes(P, N, H, W, C, S, tiles, 1, False)
+    assert a["pxb_blend_forward"] == N * 40 + 4 * 5 * H * W
+    assert a["pxb_blend_backward"] == N * 40 + 20 * H * W + N * 72
+    b = bench.algorithmic_bytes(P, N, H, W, C, S, tiles, 8, True)
+    assert a["pxb_fused_backward"] - b["pxb_fused_backward"] == P * (192 - 12)
+    assert bench.metric_name("cfg4", "train", {"W": 1920, "H": 1080}).startswith("train it/s (fwd+bwd), 1M Gaussians @1080p")
+    assert bench.metric_name("cfg4", "render", {"W": 1920, "H": 1080}).startswith("render Mpix/s")
