@@ -4,12 +4,16 @@ Drop-in for ``pointrix/model/renderer/msplat.py:12-248``: same registry entry
 name, ``Config``, ``setup``, ``render_iter`` / ``render_batch`` signatures and
 returned dict (``rendered_features_split`` / per-feature stacks, ``uv_points``,
 ``visibility``, ``radii``), ``update_sh_degree``, ``state_dict`` /
-``load_state_dict``.  One view is five kernel launches forward (fused
-per-Gaussian stage, tile scan, key emit + radix sort + ranges, blend) and two
-backward (blend backward, fused per-Gaussian backward) instead of the
-reference's ~14 kernels + ~40 torch ops; the autograd graph of ``render_iter``
-(SURVEY.md section 8a "gradient routing") is reproduced by a single
-``torch.autograd.Function``.
+``load_state_dict``.  One view is ONE foreign call forward (19 kernels queued back to
+back from native code: the fused per-Gaussian stage, 9 for the depth order of the
+visible Gaussians, 8 for key emission + tile sort + ranges, the blend) and one
+backward (blend backward, fused per-Gaussian backward) instead of the reference's
+~14 kernels + ~40 torch ops; the autograd graph of ``render_iter`` (SURVEY.md section 8a
+"gradient routing") is reproduced by a single ``torch.autograd.Function``.
+
+Beyond the reference's surface: ``render_iter_raw`` (the point cloud's raw parameters,
+activations inside the kernels), ``camera_extrinsics`` (the camera model of one view),
+``Config.sync_free`` (no host wait in ``no_grad`` forwards; CUDA-graph capturable).
 """
 from __future__ import annotations
 
